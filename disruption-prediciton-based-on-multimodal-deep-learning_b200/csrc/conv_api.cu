@@ -1,0 +1,131 @@
+// C-ABI entry points for the convolution family: validation, weight packing, dispatch between
+// the tcgen05 kernels and the CUDA-core kernels.  No cuDNN, no CPU path.
+#include "dp_common.cuh"
+#include "conv_internal.cuh"
+
+namespace dp {
+
+static int validate(const dp_conv_desc* d) {
+  DP_REQUIRE(d != nullptr, DP_ERR_SHAPE, "conv desc is NULL");
+  DP_REQUIRE(d->dtype == DP_F32 || d->dtype == DP_BF16, DP_ERR_UNSUPPORTED, "conv desc: bad dtype %d", d->dtype);
+  DP_REQUIRE(d->B > 0 && d->Ti > 0 && d->Hi > 0 && d->Wi > 0 && d->C > 0 && d->K > 0, DP_ERR_SHAPE,
+             "conv desc: non-positive dimension");
+  DP_REQUIRE(d->Cp >= d->C && d->Cp % 16 == 0 && d->Kp >= d->K && d->Kp % 16 == 0, DP_ERR_ALIGN,
+             "conv desc: padded channels must be multiples of 16 (Cp=%d Kp=%d)", d->Cp, d->Kp);
+  DP_REQUIRE(d->kt > 0 && d->kh > 0 && d->kw > 0 && d->st > 0 && d->sh > 0 && d->sw > 0, DP_ERR_SHAPE,
+             "conv desc: bad kernel/stride");
+  const int To = (d->Ti + 2 * d->pt - d->kt) / d->st + 1;
+  const int Ho = (d->Hi + 2 * d->ph - d->kh) / d->sh + 1;
+  const int Wo = (d->Wi + 2 * d->pw - d->kw) / d->sw + 1;
+  DP_REQUIRE(To == d->To && Ho == d->Ho && Wo == d->Wo && To > 0 && Ho > 0 && Wo > 0, DP_ERR_SHAPE,
+             "conv desc: output dims (%d,%d,%d) do not match geometry (%d,%d,%d)", d->To, d->Ho, d->Wo, To, Ho, Wo);
+  return DP_OK;
+}
+
+template <typename T>
+__global__ void pack_weights_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd,
+                                    int K, int C, int Kp, int Cp, int taps) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)Kp * taps * Cp;
+  if (idx >= total) return;
+  const int c = (int)(idx % Cp), tap = (int)((idx / Cp) % taps), n = (int)(idx / ((int64_t)Cp * taps));
+  float v = 0.f;
+  if (n < K && c < C) v = w[((int64_t)n * C + c) * taps + tap];
+  if (wf != nullptr) wf[idx] = (T)v;
+  if (wd != nullptr) wd[((int64_t)c * taps + tap) * Kp + n] = (T)v;
+}
+
+static int resolve_impl(const dp_conv_desc* d, int op, int impl) {
+  if (impl == DP_IMPL_SIMT) return DP_IMPL_SIMT;
+  bool ok = false;
+  if (d->dtype == DP_BF16) {
+    if (op == 0) ok = tc_fwd_supported(d);
+    else if (op == 1) ok = tc_dgrad_supported(d);
+    else ok = tc_wgrad_supported(d);
+  }
+  if (impl == DP_IMPL_TC) return ok ? DP_IMPL_TC : -1;
+  return ok ? DP_IMPL_TC : DP_IMPL_SIMT;
+}
+
+}  // namespace dp
+
+using namespace dp;
+
+DP_API int dp_pack_weights(const dp_conv_desc* d, const float* w, void* w_fwd, void* w_dgrad, void* stream) {
+  int rc = validate(d);
+  if (rc != DP_OK) return rc;
+  DP_REQUIRE(w != nullptr, DP_ERR_SHAPE, "dp_pack_weights: NULL weight");
+  const int taps = d->kt * d->kh * d->kw;
+  const int64_t total = (int64_t)d->Kp * taps * d->Cp;
+  const int grid = ceil_div(total, 256);
+  if (d->dtype == DP_BF16)
+    pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(
+        w, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad, d->K, d->C, d->Kp, d->Cp, taps);
+  else
+    pack_weights_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(w, (float*)w_fwd, (float*)w_dgrad, d->K, d->C,
+                                                                    d->Kp, d->Cp, taps);
+  return check_launch("dp_pack_weights");
+}
+
+DP_API int dp_conv_supported(const dp_conv_desc* d, int op, int impl) {
+  if (validate(d) != DP_OK) return 0;
+  if (op < 0 || op > 2) return 0;
+  return resolve_impl(d, op, impl) > 0 ? 1 : 0;
+}
+
+DP_API int dp_conv_fwd(const dp_conv_desc* d, const void* x, const void* w_fwd, void* y, float* part, int* nparts,
+                       int impl, void* stream) {
+  int rc = validate(d);
+  if (rc != DP_OK) return rc;
+  DP_REQUIRE(x && w_fwd && y, DP_ERR_SHAPE, "dp_conv_fwd: NULL pointer");
+  DP_REQUIRE(part == nullptr || nparts != nullptr, DP_ERR_SHAPE, "dp_conv_fwd: part given without nparts");
+  const int r = resolve_impl(d, 0, impl);
+  DP_REQUIRE(r > 0, DP_ERR_UNSUPPORTED, "dp_conv_fwd: geometry not covered by the tcgen05 family");
+  cudaStream_t s = as_stream(stream);
+  if (r == DP_IMPL_TC) return tc_conv_fwd(d, x, w_fwd, y, part, nparts, s);
+  rc = simt_conv_fwd(d, x, w_fwd, y, s);
+  if (rc != DP_OK) return rc;
+  if (part != nullptr) {
+    const int64_t rows = (int64_t)d->B * d->To * d->Ho * d->Wo;
+    return bn_stats_launch(y, rows, d->Kp, d->dtype, part, nparts, s);
+  }
+  return DP_OK;
+}
+
+DP_API int dp_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx,
+                         int impl, void* stream) {
+  int rc = validate(d);
+  if (rc != DP_OK) return rc;
+  DP_REQUIRE(dy && w_dgrad && dx, DP_ERR_SHAPE, "dp_conv_dgrad: NULL pointer");
+  const int r = resolve_impl(d, 1, impl);
+  DP_REQUIRE(r > 0, DP_ERR_UNSUPPORTED, "dp_conv_dgrad: geometry not covered by the tcgen05 family");
+  cudaStream_t s = as_stream(stream);
+  if (r == DP_IMPL_TC) return tc_conv_dgrad(d, dy, w_dgrad, addend, dx, s);
+  return simt_conv_dgrad(d, dy, w_dgrad, addend, dx, s);
+}
+
+DP_API size_t dp_conv_wgrad_workspace(const dp_conv_desc* d, int impl) {
+  if (validate(d) != DP_OK) return 0;
+  size_t a = simt_wgrad_workspace(d);
+  if (impl != DP_IMPL_SIMT && d->dtype == DP_BF16 && tc_wgrad_supported(d)) {
+    size_t b = tc_wgrad_workspace(d);
+    if (b > a) a = b;
+  }
+  return a;
+}
+
+DP_API int dp_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw, void* workspace,
+                         size_t workspace_bytes, int impl, void* stream) {
+  int rc = validate(d);
+  if (rc != DP_OK) return rc;
+  DP_REQUIRE(x && dy && dw && workspace, DP_ERR_SHAPE, "dp_conv_wgrad: NULL pointer");
+  const int r = resolve_impl(d, 2, impl);
+  DP_REQUIRE(r > 0, DP_ERR_UNSUPPORTED, "dp_conv_wgrad: geometry not covered by the tcgen05 family");
+  cudaStream_t s = as_stream(stream);
+  if (r == DP_IMPL_TC) {
+    DP_REQUIRE(workspace_bytes >= tc_wgrad_workspace(d), DP_ERR_SHAPE, "dp_conv_wgrad: workspace too small");
+    return tc_conv_wgrad(d, x, dy, dw, workspace, workspace_bytes, s);
+  }
+  DP_REQUIRE(workspace_bytes >= simt_wgrad_workspace(d), DP_ERR_SHAPE, "dp_conv_wgrad: workspace too small");
+  return simt_conv_wgrad(d, x, dy, dw, workspace, s);
+}

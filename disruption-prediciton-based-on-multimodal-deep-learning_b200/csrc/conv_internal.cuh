@@ -1,0 +1,31 @@
+// Internal (non-ABI) launchers shared between the conv translation units.
+#pragma once
+#include "dp_common.cuh"
+
+namespace dp {
+
+// CUDA-core family (conv_simt.cu)
+int simt_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s);
+int simt_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
+                    cudaStream_t s);
+int simt_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw, void* ws,
+                    cudaStream_t s);
+size_t simt_wgrad_workspace(const dp_conv_desc* d);
+
+// tcgen05 family (conv_tc.cu / wgrad_tc.cu)
+bool tc_fwd_supported(const dp_conv_desc* d);
+bool tc_dgrad_supported(const dp_conv_desc* d);
+bool tc_wgrad_supported(const dp_conv_desc* d);
+// writes BN partials when part != nullptr; *nparts receives the row count
+int tc_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, float* part, int* nparts,
+                cudaStream_t s);
+int tc_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
+                  cudaStream_t s);
+size_t tc_wgrad_workspace(const dp_conv_desc* d);
+int tc_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
+                  cudaStream_t s);
+
+// BN partial statistics over a finished tensor (bn_act.cu)
+int bn_stats_launch(const void* y, int64_t rows, int Cp, int dtype, float* part, int* nparts, cudaStream_t s);
+
+}  // namespace dp

@@ -1,0 +1,564 @@
+// tcgen05 / TMEM / TMA implicit-GEMM "gather GEMM" for the (2+1)D convolutions, bf16 in, fp32 accumulate.
+//
+//   dst[pixel][n] = sum_{tap, r} src[pixel * stride + offset(tap)][r] * wgt[n][tap][r]
+//
+// used as  forward  (src = x,  wgt = w_fwd  [Kp][taps][Cp], dst = y,  BN statistics in the epilogue)
+// and as   dgrad    (src = dy, wgt = w_dgrad[Cp][taps][Kp], dst = dx, taps flipped, optional addend)
+// for the nn.Conv3d calls at /root/reference/src/models/R2Plus1D.py:44-51,57 and their autograd.
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0 lane 0 : TMA producer. NDHWC activations are a 5-D tensor map (C,W,H,T,B); one box =
+//                   128 output pixels (bw x bh x bt) x CB channels, zero-filled outside the tensor, so
+//                   padding costs nothing.  Stride-1 convs load ONE halo box per kw (or one for all
+//                   kt) and reuse it for the kh (kt) taps by moving the UMMA descriptor start row.
+//   warp 1 lane 0 : issues tcgen05.mma (M=128, N=Ntile<=256, K=16) into a double-buffered TMEM
+//                   accumulator; tcgen05.commit releases smem stages and publishes the accumulator.
+//   warp 2        : TMEM allocate / free.
+//   warps 4-7     : epilogue: tcgen05.ld -> (+addend) -> bf16 -> smem staging -> TMA store (clips the
+//                   tensor edge), per-channel sum / sum-of-squares for BatchNorm from the staged tile.
+#include "dp_common.cuh"
+#include "conv_internal.cuh"
+#include "tc_ptx.cuh"
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+
+namespace dp {
+using namespace ptx;
+
+constexpr int TC_MAX_LOADS = 49;
+constexpr int TC_THREADS = 256;
+constexpr int TC_EPI = 128;
+constexpr int TC_SMEM_MAX = 232448;  // 227 KB opt-in limit per CTA
+
+struct TcParams {
+  int B, ntile_w, ntile_h, ntile_t, n_ntiles, num_tiles;
+  int bw, bh, bt;
+  int dW, dH, dT, dC;       // destination dims / padded channels
+  int mw, mh, mt;           // source coordinate multipliers (conv stride)
+  int nloads, nsub, ncblk, CB, ksteps_last;
+  int sub_row_bytes, tap_sub_stride, red_C;
+  int Ntile;
+  int a_box_bytes, b_box_bytes, b_sub_bytes, stage_bytes, num_stages;
+  int off_staging, off_stats, off_scratch, off_bars;
+  int tmem_cols, layout_type, sbo_bytes;
+  int has_stats, has_addend;
+  signed char off_w[TC_MAX_LOADS], off_h[TC_MAX_LOADS], off_t[TC_MAX_LOADS];
+  short tap0[TC_MAX_LOADS];
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmD, const __grid_constant__ TcParams p,
+                      const __nv_bfloat16* __restrict__ addend, float* __restrict__ part) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (sbase - raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.num_stages;
+  const uint32_t bars = sbase + p.off_bars;
+  auto full_bar = [&](int i) { return bars + 8u * i; };
+  auto empty_bar = [&](int i) { return bars + 8u * (S + i); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.off_bars + 8 * (2 * S + 4));
+  float* stats_sm = reinterpret_cast<float*>(sm + p.off_stats);
+  float* scratch = reinterpret_cast<float*>(sm + p.off_scratch);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    for (int i = 0; i < S; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI); }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(sbase + p.off_bars + 8 * (2 * S + 4), (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  if (threadIdx.x >= TC_THREADS - TC_EPI) {
+    for (int i = threadIdx.x - (TC_THREADS - TC_EPI); i < 2 * p.dC; i += TC_EPI) stats_sm[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int kiters = p.nloads * p.ncblk;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int n_idx = r % p.n_ntiles; r /= p.n_ntiles;
+      const int tw = r % p.ntile_w; r /= p.ntile_w;
+      const int th = r % p.ntile_h; r /= p.ntile_h;
+      const int tt = r % p.ntile_t; r /= p.ntile_t;
+      const int b = r;
+      const int w0 = tw * p.bw * p.mw, h0 = th * p.bh * p.mh, t0 = tt * p.bt * p.mt;
+      for (int l = 0; l < p.nloads; ++l) {
+        for (int cb = 0; cb < p.ncblk; ++cb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = sbase + (uint32_t)stage * p.stage_bytes;
+          mbar_expect_tx(full_bar(stage), (uint32_t)(p.a_box_bytes + p.nsub * p.b_box_bytes));
+          tma_load_5d(&tmA, full_bar(stage), sa, cb * p.CB, w0 + p.off_w[l], h0 + p.off_h[l], t0 + p.off_t[l], b);
+          for (int s = 0; s < p.nsub; ++s) {
+            const int tap = p.tap0[l] + s * p.tap_sub_stride;
+            tma_load_2d(&tmB, full_bar(stage), sa + p.stage_bytes - (p.nsub - s) * p.b_sub_bytes,
+                        tap * p.red_C + cb * p.CB, n_idx * p.Ntile);
+          }
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_bf16(128, p.Ntile, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Ntile);
+      uint32_t accumulate = 0;
+      for (int it = 0; it < kiters; ++it) {
+        const int cb = it % p.ncblk;
+        const int ksteps = (cb == p.ncblk - 1) ? p.ksteps_last : (p.CB >> 4);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = sbase + (uint32_t)stage * p.stage_bytes;
+        for (int s = 0; s < p.nsub; ++s) {
+          const uint32_t a_addr = sa + (uint32_t)(s * p.sub_row_bytes);
+          const uint32_t b_addr = sa + p.stage_bytes - (p.nsub - s) * p.b_sub_bytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = make_smem_desc(a_addr + 32u * k, 16, (uint32_t)p.sbo_bytes, (uint32_t)p.layout_type);
+            const uint64_t bdesc = make_smem_desc(b_addr + 32u * k, 16, (uint32_t)p.sbo_bytes, (uint32_t)p.layout_type);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+            accumulate = 1;
+          }
+        }
+        umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar(acc));      // accumulator complete -> epilogue
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int e = threadIdx.x - (TC_THREADS - TC_EPI);  // 0..127 == accumulator row == TMEM lane
+    const int q = warp & 3;
+    uint8_t* staging = sm + p.off_staging;
+    const uint32_t staging_s = sbase + p.off_staging;
+    const int row_bytes = p.Ntile * 2;
+    const int lw = e % p.bw, lh = (e / p.bw) % p.bh, lt = e / (p.bw * p.bh);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int n_idx = r % p.n_ntiles; r /= p.n_ntiles;
+      const int tw = r % p.ntile_w; r /= p.ntile_w;
+      const int th = r % p.ntile_h; r /= p.ntile_h;
+      const int tt = r % p.ntile_t; r /= p.ntile_t;
+      const int b = r;
+      const int w = tw * p.bw + lw, h = th * p.bh + lh, t = tt * p.bt + lt;
+      const bool valid = (w < p.dW) && (h < p.dH) && (t < p.dT);
+      const __nv_bfloat16* arow = nullptr;
+      if (p.has_addend && valid)
+        arow = addend + ((((int64_t)b * p.dT + t) * p.dH + h) * p.dW + w) * p.dC + n_idx * p.Ntile;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      if (e == 0) tma_store_wait_read();  // previous tile's TMA store has finished reading the staging tile
+      named_bar_sync(1, TC_EPI);
+
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * p.Ntile) + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.Ntile; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = valid ? __uint_as_float(v[j]) : 0.f;
+        if (arow != nullptr) {
+          const f8 a0 = ld8(arow + c0), a1 = ld8(arow + c0 + 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { f[j] += a0.v[j]; f[8 + j] += a1.v[j]; }
+        }
+        uint4 o0, o1;
+        __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          h1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+        }
+        uint4* dstp = reinterpret_cast<uint4*>(staging + (size_t)e * row_bytes + c0 * 2);
+        dstp[0] = o0;
+        dstp[1] = o1;
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      fence_proxy_async_smem();
+      named_bar_sync(1, TC_EPI);
+      if (e == 0) {
+        tma_store_5d(&tmD, staging_s, n_idx * p.Ntile, tw * p.bw, th * p.bh, tt * p.bt, b);
+        tma_store_commit();
+      }
+      if (p.has_stats) {
+        const int ncp = p.Ntile >> 1;
+        const int nrg = TC_EPI / ncp;
+        const int cp = e % ncp, rg = e / ncp;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        if (rg < nrg) {
+          const uint32_t* st32 = reinterpret_cast<const uint32_t*>(staging);
+          for (int row = rg; row < 128; row += nrg) {
+            uint32_t wv = st32[row * ncp + cp];
+            const float2 fv = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&wv));
+            s0 += fv.x; s1 += fv.y;
+            q0 = fmaf(fv.x, fv.x, q0); q1 = fmaf(fv.y, fv.y, q1);
+          }
+        }
+        scratch[e * 4 + 0] = s0; scratch[e * 4 + 1] = s1; scratch[e * 4 + 2] = q0; scratch[e * 4 + 3] = q1;
+        named_bar_sync(2, TC_EPI);
+        if (e < ncp) {
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+          for (int g = 0; g < nrg; ++g) {
+            const float* sp = scratch + (g * ncp + e) * 4;
+            a0 += sp[0]; a1 += sp[1]; b0 += sp[2]; b1 += sp[3];
+          }
+          const int c = n_idx * p.Ntile + 2 * e;
+          stats_sm[c] += a0; stats_sm[c + 1] += a1;
+          stats_sm[p.dC + c] += b0; stats_sm[p.dC + c + 1] += b1;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (e == 0) tma_store_wait_all();
+    if (p.has_stats) {
+      named_bar_sync(1, TC_EPI);
+      for (int i = e; i < 2 * p.dC; i += TC_EPI) part[(int64_t)blockIdx.x * 2 * p.dC + i] = stats_sm[i];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: planning + tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)ptr;
+  });
+  return fn;
+}
+
+static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1;
+int tc_option(const char* name, int value, bool set) {
+  int* slot = nullptr;
+  if (!strcmp(name, "tc_halo")) slot = &g_opt_halo;
+  else if (!strcmp(name, "tc_strided")) slot = &g_opt_strided;
+  else if (!strcmp(name, "tc_max_stages")) slot = &g_opt_max_stages;
+  else if (!strcmp(name, "tc_enable")) slot = &g_opt_tc;
+  if (slot == nullptr) return -1;
+  if (set) *slot = value;
+  return *slot;
+}
+
+// Role-agnostic problem: forward or stride-1 dgrad.
+struct GatherProblem {
+  int B;
+  int sT, sH, sW, sC;
+  int dT, dH, dW, dC;
+  int kt, kh, kw;
+  int mt, mh, mw;
+  int ot, oh, ow;  // source coordinate offset of tap position j = 0
+  bool flip;       // weight tap for position j is (k-1-j)
+};
+
+struct TcPlan {
+  TcParams p;
+  int grid;
+  size_t smem;
+  int a_box[5];
+  int a_estride[5];
+};
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
+  if (!g_opt_tc) return false;
+  const int taps = g.kt * g.kh * g.kw;
+  if (taps > TC_MAX_LOADS) return false;
+  if (g.sC % 16 || g.dC % 16) return false;
+  const bool strided = (g.mt != 1 || g.mh != 1 || g.mw != 1);
+  if (strided && !g_opt_strided) return false;
+  if (g.mt > 8 || g.mh > 8 || g.mw > 8) return false;
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  // N tiling
+  p.n_ntiles = (g.dC + 255) / 256;
+  if (g.dC % (16 * p.n_ntiles)) return false;
+  p.Ntile = g.dC / p.n_ntiles;
+  // K blocking
+  p.CB = g.sC <= 16 ? 16 : (g.sC <= 32 ? 32 : 64);
+  p.ncblk = (g.sC + p.CB - 1) / p.CB;
+  p.ksteps_last = (g.sC - (p.ncblk - 1) * p.CB) / 16;
+  p.layout_type = p.CB == 64 ? 2 : (p.CB == 32 ? 4 : 6);
+  const int rowbytes = p.CB * 2;
+  p.sbo_bytes = 8 * rowbytes;
+  p.red_C = g.sC;
+  p.b_box_bytes = p.Ntile * rowbytes;
+  p.b_sub_bytes = round_up(p.b_box_bytes, 1024);
+  const int staging_bytes = round_up(128 * p.Ntile * 2, 1024);
+  const int stats_bytes = round_up(2 * g.dC * 4, 16);
+  const int fixed = staging_bytes + stats_bytes + 2048 + 256 + 1024;
+
+  // tile / mode search
+  double best = 1e30;
+  int best_mode = -1, best_bw = 0, best_bh = 0, best_bt = 0;
+  for (int mode = 0; mode < 3; ++mode) {
+    if (mode == 1 && !(g_opt_halo && !strided && g.kt == 1 && g.kh > 1)) continue;
+    if (mode == 2 && !(g_opt_halo && !strided && g.kh == 1 && g.kw == 1 && g.kt > 1)) continue;
+    for (int bw = 1; bw <= 128; bw <<= 1) {
+      for (int bh = 1; bh * bw <= 128; bh <<= 1) {
+        const int bt = 128 / (bw * bh);
+        if (mode == 1 && (bt != 1 || bw % 8)) continue;
+        if (mode == 2 && ((bw * bh) % 8)) continue;
+        if (bw * g.mw > 256 || bh * g.mh > 256 || bt * g.mt > 256) continue;
+        // do not take tiles that are mostly outside the tensor
+        if (bw > 2 * g.dW && bw > 8) continue;
+        if (bh >= 2 * g.dH && bh > 1) continue;
+        if (bt >= 2 * g.dT && bt > 1) continue;
+        int rows_l = 128, nloads = taps, nsub = 1;
+        if (mode == 1) { rows_l = (bh + g.kh - 1) * bw; nloads = g.kw; nsub = g.kh; if (bh + g.kh - 1 > 256) continue; }
+        if (mode == 2) { rows_l = (bt + g.kt - 1) * bh * bw; nloads = 1; nsub = g.kt; if (bt + g.kt - 1 > 256) continue; }
+        const int stage = round_up(rows_l * rowbytes, 1024) + nsub * p.b_sub_bytes;
+        if (fixed + 2 * stage > TC_SMEM_MAX) continue;
+        const double ntiles = (double)((g.dW + bw - 1) / bw) * ((g.dH + bh - 1) / bh) * ((g.dT + bt - 1) / bt);
+        const double cost = ntiles * ((double)nloads * p.ncblk * (rows_l * rowbytes + nsub * p.b_box_bytes) +
+                                      0.15 * taps * 128.0 * g.sC * 2.0) - 1e-3 * bw;
+        if (cost < best) { best = cost; best_mode = mode; best_bw = bw; best_bh = bh; best_bt = bt; }
+      }
+    }
+  }
+  if (best_mode < 0) return false;
+  p.bw = best_bw; p.bh = best_bh; p.bt = best_bt;
+  p.B = g.B;
+  p.ntile_w = (g.dW + p.bw - 1) / p.bw;
+  p.ntile_h = (g.dH + p.bh - 1) / p.bh;
+  p.ntile_t = (g.dT + p.bt - 1) / p.bt;
+  const int64_t nt = (int64_t)g.B * p.ntile_w * p.ntile_h * p.ntile_t * p.n_ntiles;
+  if (nt > 0x7fffffff) return false;
+  p.num_tiles = (int)nt;
+  p.dW = g.dW; p.dH = g.dH; p.dT = g.dT; p.dC = g.dC;
+  p.mw = g.mw; p.mh = g.mh; p.mt = g.mt;
+
+  int rows_l = 128;
+  out->a_estride[0] = 1; out->a_estride[1] = g.mw; out->a_estride[2] = g.mh; out->a_estride[3] = g.mt; out->a_estride[4] = 1;
+  out->a_box[0] = p.CB; out->a_box[4] = 1;
+  auto tap_index = [&](int jt, int jh, int jw) {
+    if (g.flip) { jt = g.kt - 1 - jt; jh = g.kh - 1 - jh; jw = g.kw - 1 - jw; }
+    return (jt * g.kh + jh) * g.kw + jw;
+  };
+  if (best_mode == 0) {
+    p.nloads = taps; p.nsub = 1; p.sub_row_bytes = 0; p.tap_sub_stride = 0;
+    int l = 0;
+    for (int jt = 0; jt < g.kt; ++jt)
+      for (int jh = 0; jh < g.kh; ++jh)
+        for (int jw = 0; jw < g.kw; ++jw, ++l) {
+          p.off_t[l] = (signed char)(g.ot + jt); p.off_h[l] = (signed char)(g.oh + jh); p.off_w[l] = (signed char)(g.ow + jw);
+          p.tap0[l] = (short)tap_index(jt, jh, jw);
+        }
+    out->a_box[1] = p.bw * g.mw; out->a_box[2] = p.bh * g.mh; out->a_box[3] = p.bt * g.mt;
+  } else if (best_mode == 1) {
+    p.nloads = g.kw; p.nsub = g.kh; p.sub_row_bytes = p.bw * rowbytes;
+    p.tap_sub_stride = tap_index(0, 1, 0) - tap_index(0, 0, 0);
+    for (int jw = 0; jw < g.kw; ++jw) {
+      p.off_t[jw] = (signed char)g.ot; p.off_h[jw] = (signed char)g.oh; p.off_w[jw] = (signed char)(g.ow + jw);
+      p.tap0[jw] = (short)tap_index(0, 0, jw);
+    }
+    rows_l = (p.bh + g.kh - 1) * p.bw;
+    out->a_box[1] = p.bw; out->a_box[2] = p.bh + g.kh - 1; out->a_box[3] = 1;
+  } else {
+    p.nloads = 1; p.nsub = g.kt; p.sub_row_bytes = p.bw * p.bh * rowbytes;
+    p.tap_sub_stride = tap_index(1, 0, 0) - tap_index(0, 0, 0);
+    p.off_t[0] = (signed char)g.ot; p.off_h[0] = (signed char)g.oh; p.off_w[0] = (signed char)g.ow;
+    p.tap0[0] = (short)tap_index(0, 0, 0);
+    rows_l = (p.bt + g.kt - 1) * p.bh * p.bw;
+    out->a_box[1] = p.bw; out->a_box[2] = p.bh; out->a_box[3] = p.bt + g.kt - 1;
+  }
+  p.a_box_bytes = rows_l * rowbytes;
+  p.stage_bytes = round_up(p.a_box_bytes, 1024) + p.nsub * p.b_sub_bytes;
+  int stages = (TC_SMEM_MAX - fixed) / p.stage_bytes;
+  if (stages > g_opt_max_stages) stages = g_opt_max_stages;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return false;
+  p.num_stages = stages;
+  p.off_staging = stages * p.stage_bytes;
+  p.off_stats = p.off_staging + staging_bytes;
+  p.off_scratch = p.off_stats + stats_bytes;
+  p.off_bars = p.off_scratch + 2048;
+  int cols = 32;
+  while (cols < 2 * p.Ntile) cols <<= 1;
+  if (cols > 512) return false;
+  p.tmem_cols = cols;
+  p.has_stats = has_stats ? 1 : 0;
+  out->p = p;
+  out->smem = (size_t)p.off_bars + 256 + 1024;
+  const int sms = num_sms();
+  out->grid = p.num_tiles < sms ? p.num_tiles : sms;
+  return out->smem <= (size_t)TC_SMEM_MAX;
+}
+
+static int encode_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, const int* box,
+                          const int* estride, CUtensorMapSwizzle sw) {
+  PFN_encodeTiled enc = get_encode();
+  DP_REQUIRE(enc != nullptr, DP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)T * H * W * C * 2};
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < 5; ++i) { b[i] = (cuuint32_t)box[i]; es[i] = (cuuint32_t)estride[i]; }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, b, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DP_REQUIRE(r == CUDA_SUCCESS, DP_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed: CUresult %d (box %d,%d,%d,%d)",
+             (int)r, box[0], box[1], box[2], box[3]);
+  return DP_OK;
+}
+
+static int encode_wgt_map(CUtensorMap* m, const void* ptr, int Ktot, int rows, int boxK, int boxN,
+                          CUtensorMapSwizzle sw) {
+  PFN_encodeTiled enc = get_encode();
+  DP_REQUIRE(enc != nullptr, DP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t b[2] = {(cuuint32_t)boxK, (cuuint32_t)boxN};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, b, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DP_REQUIRE(r == CUDA_SUCCESS, DP_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: CUresult %d", (int)r);
+  return DP_OK;
+}
+
+static int launch_gather(const GatherProblem& g, const void* src, const void* wgt, void* dst, const void* addend,
+                         float* part, int* nparts, cudaStream_t s) {
+  TcPlan plan;
+  DP_REQUIRE(plan_gather(g, part != nullptr, &plan), DP_ERR_UNSUPPORTED, "tcgen05 conv: geometry not supported");
+  DP_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)wgt & 15) == 0 && ((uintptr_t)dst & 15) == 0, DP_ERR_ALIGN,
+             "tcgen05 conv: tensors must be 16-byte aligned");
+  TcParams& p = plan.p;
+  p.has_addend = addend != nullptr ? 1 : 0;
+  const CUtensorMapSwizzle sw = p.CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                           : (p.CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap tmA, tmB, tmD;
+  int rc = encode_act_map(&tmA, src, g.sC, g.sW, g.sH, g.sT, g.B, plan.a_box, plan.a_estride, sw);
+  if (rc != DP_OK) return rc;
+  const int taps = g.kt * g.kh * g.kw;
+  rc = encode_wgt_map(&tmB, wgt, taps * g.sC, g.dC, p.CB, p.Ntile, sw);
+  if (rc != DP_OK) return rc;
+  const int dbox[5] = {p.Ntile, p.bw, p.bh, p.bt, 1};
+  const int ones[5] = {1, 1, 1, 1, 1};
+  rc = encode_act_map(&tmD, dst, g.dC, g.dW, g.dH, g.dT, g.B, dbox, ones, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc != DP_OK) return rc;
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(tc_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+  });
+  DP_REQUIRE(attr_err == cudaSuccess, DP_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s",
+             cudaGetErrorString(attr_err));
+  tc_gather_gemm_kernel<<<plan.grid, TC_THREADS, plan.smem, s>>>(tmA, tmB, tmD, p, (const __nv_bfloat16*)addend, part);
+  if (nparts != nullptr) *nparts = plan.grid;
+  return check_launch("tc_gather_gemm_kernel");
+}
+
+static GatherProblem fwd_problem(const dp_conv_desc* d) {
+  GatherProblem g;
+  g.B = d->B;
+  g.sT = d->Ti; g.sH = d->Hi; g.sW = d->Wi; g.sC = d->Cp;
+  g.dT = d->To; g.dH = d->Ho; g.dW = d->Wo; g.dC = d->Kp;
+  g.kt = d->kt; g.kh = d->kh; g.kw = d->kw;
+  g.mt = d->st; g.mh = d->sh; g.mw = d->sw;
+  g.ot = -d->pt; g.oh = -d->ph; g.ow = -d->pw;
+  g.flip = false;
+  return g;
+}
+
+static bool dgrad_problem(const dp_conv_desc* d, GatherProblem* g) {
+  if (d->st != 1 || d->sh != 1 || d->sw != 1) return false;
+  if (d->To != d->Ti || d->Ho != d->Hi || d->Wo != d->Wi) return false;
+  g->B = d->B;
+  g->sT = d->To; g->sH = d->Ho; g->sW = d->Wo; g->sC = d->Kp;
+  g->dT = d->Ti; g->dH = d->Hi; g->dW = d->Wi; g->dC = d->Cp;
+  g->kt = d->kt; g->kh = d->kh; g->kw = d->kw;
+  g->mt = g->mh = g->mw = 1;
+  g->ot = d->pt - (d->kt - 1); g->oh = d->ph - (d->kh - 1); g->ow = d->pw - (d->kw - 1);
+  g->flip = true;
+  return true;
+}
+
+bool tc_fwd_supported(const dp_conv_desc* d) {
+  if (d->dtype != DP_BF16) return false;
+  TcPlan plan;
+  return plan_gather(fwd_problem(d), true, &plan);
+}
+
+bool tc_dgrad_supported(const dp_conv_desc* d) {
+  if (d->dtype != DP_BF16) return false;
+  GatherProblem g;
+  if (!dgrad_problem(d, &g)) return false;
+  TcPlan plan;
+  return plan_gather(g, false, &plan);
+}
+
+int tc_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, float* part, int* nparts,
+                cudaStream_t s) {
+  return launch_gather(fwd_problem(d), x, w, y, nullptr, part, nparts, s);
+}
+
+int tc_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
+                  cudaStream_t s) {
+  GatherProblem g;
+  DP_REQUIRE(dgrad_problem(d, &g), DP_ERR_UNSUPPORTED, "tcgen05 dgrad: strided geometry not supported");
+  return launch_gather(g, dy, w, dx, addend, nullptr, nullptr, s);
+}
+
+}  // namespace dp
+
+DP_API int dp_set_option(const char* name, int value) {
+  if (name == nullptr) return DP_ERR_SHAPE;
+  return dp::tc_option(name, value, true) < 0 ? DP_ERR_UNSUPPORTED : DP_OK;
+}
+DP_API int dp_get_option(const char* name) {
+  if (name == nullptr) return -1;
+  return dp::tc_option(name, 0, false);
+}

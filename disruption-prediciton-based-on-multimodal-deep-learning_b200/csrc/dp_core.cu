@@ -1,0 +1,49 @@
+// Library-level entry points: version, error text, device capability.
+#include "dp_common.cuh"
+#include <string.h>
+
+namespace dp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cached = n;
+  return n;
+}
+
+}  // namespace dp
+
+DP_API int dp_version(void) { return 100; }
+
+DP_API const char* dp_last_error(void) { return dp::g_err; }
+
+DP_API int dp_num_sms(void) { return dp::num_sms(); }
+
+DP_API int dp_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    dp::set_error("cudaGetDevice: %s", cudaGetErrorString(e));
+    return DP_ERR_CUDA;
+  }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) {
+    dp::set_error("device %d is sm_%d%d; this library holds sm_100a code only", dev, major, minor);
+    return DP_ERR_ARCH;
+  }
+  return DP_OK;
+}

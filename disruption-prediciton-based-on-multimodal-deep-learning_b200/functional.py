@@ -1,0 +1,553 @@
+"""Host-side plumbing between PyTorch autograd and the C ABI (libdp_b200.so).
+
+Everything numerical happens in the CUDA kernels; this file owns
+  * the internal activation format: a plain torch tensor (B,T,H,W,Cp), bf16 (product path) or
+    fp32 (validation mode), channel-padded with zeros to a multiple of 16, tagged with `_dp_c`
+    (logical channel count);
+  * one "layer" = Conv3d -> BatchNorm3d -> LeakyReLU [-> + residual -> LeakyReLU]
+    (reference: Conv3dBlock, /root/reference/src/models/R2Plus1D.py:25-58; residual tail :181-187);
+  * torch.autograd.Function wrappers at layer and residual-block granularity.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+_STATE = {"dtype": torch.bfloat16, "impl": L.IMPL_AUTO}
+
+
+def set_compute_mode(mode: str) -> None:
+    """'bf16' = product path (bf16 storage, fp32 accumulate); 'fp32' = validation mode."""
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("mode must be 'bf16' or 'fp32'")
+    _STATE["dtype"] = torch.bfloat16 if mode == "bf16" else torch.float32
+
+
+def get_compute_mode() -> str:
+    return "bf16" if _STATE["dtype"] == torch.bfloat16 else "fp32"
+
+
+def set_conv_impl(impl: str) -> None:
+    """'auto' | 'simt' | 'tc' -- which kernel family the conv entry points use."""
+    _STATE["impl"] = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tc": L.IMPL_TC}[impl]
+
+
+@contextlib.contextmanager
+def compute_mode(mode: str, impl: Optional[str] = None):
+    old = dict(_STATE)
+    set_compute_mode(mode)
+    if impl is not None:
+        set_conv_impl(impl)
+    try:
+        yield
+    finally:
+        _STATE.update(old)
+
+
+def ceil16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+def _code(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return L.DP_BF16
+    if t.dtype == torch.float32:
+        return L.DP_F32
+    raise L.DpError(f"unsupported activation dtype {t.dtype}")
+
+
+def tag(t: torch.Tensor, c: int) -> torch.Tensor:
+    t._dp_c = c
+    return t
+
+
+def is_internal(t) -> bool:
+    return isinstance(t, torch.Tensor) and getattr(t, "_dp_c", None) is not None
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------------------------
+# geometry cache
+# ----------------------------------------------------------------------------------------------
+class ConvGeom:
+    __slots__ = ("desc", "rows_out", "rows_in", "out_shape", "in_shape", "taps", "ws_bytes", "key")
+
+    def __init__(self, C_in, K, kernel, stride, padding, B, T, H, W, dtype_code):
+        kt, kh, kw = kernel
+        st, sh, sw = stride
+        pt, ph, pw = padding
+        To = (T + 2 * pt - kt) // st + 1
+        Ho = (H + 2 * ph - kh) // sh + 1
+        Wo = (W + 2 * pw - kw) // sw + 1
+        if min(To, Ho, Wo) <= 0:
+            raise L.DpError(f"conv geometry gives empty output: in {(T, H, W)} k {kernel} s {stride} p {padding}")
+        self.desc = L.ConvDesc(B, T, H, W, C_in, ceil16(C_in), To, Ho, Wo, K, ceil16(K), kt, kh, kw, st, sh, sw,
+                               pt, ph, pw, dtype_code)
+        self.rows_out = B * To * Ho * Wo
+        self.rows_in = B * T * H * W
+        self.out_shape = (B, To, Ho, Wo, ceil16(K))
+        self.in_shape = (B, T, H, W, ceil16(C_in))
+        self.taps = kt * kh * kw
+        self.ws_bytes = None
+
+
+_GEOMS = {}
+
+
+def conv_geom(C_in, K, kernel, stride, padding, x: torch.Tensor) -> ConvGeom:
+    B, T, H, W, Cp = x.shape
+    key = (C_in, K, kernel, stride, padding, B, T, H, W, x.dtype)
+    g = _GEOMS.get(key)
+    if g is None:
+        if Cp != ceil16(C_in):
+            raise L.DpError(f"activation has {Cp} padded channels, conv expects {ceil16(C_in)} ({C_in} logical)")
+        g = ConvGeom(C_in, K, kernel, stride, padding, B, T, H, W, _code(x))
+        _GEOMS[key] = g
+    return g
+
+
+_WS = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.index, "ws")
+    t = _WS.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = t
+    return t
+
+
+def _zeros_ws(name: str, nbytes: int, device) -> torch.Tensor:
+    """Persistent zero-initialised workspace (self-resetting kernels rely on it)."""
+    key = (device.index, name)
+    t = _WS.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _WS[key] = t
+    return t
+
+
+# ----------------------------------------------------------------------------------------------
+# layout
+# ----------------------------------------------------------------------------------------------
+def _to_internal_raw(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    L.require_device()
+    if x.dim() != 5 or x.dtype != torch.float32 or not x.is_cuda:
+        raise L.DpError(f"expected a CUDA float32 NCDHW tensor, got {tuple(x.shape)} {x.dtype} on {x.device}")
+    x = x.contiguous()
+    B, Cc, T, H, W = x.shape
+    Cp = ceil16(Cc)
+    out = torch.empty((B, T, H, W, Cp), dtype=dtype, device=x.device)
+    code = L.DP_BF16 if dtype == torch.bfloat16 else L.DP_F32
+    L.check(L.load().dp_ncdhw_f32_to_ndhwc(x.data_ptr(), out.data_ptr(), B, Cc, Cp, T, H, W, code, L.stream_ptr()),
+            "dp_ncdhw_f32_to_ndhwc")
+    return out
+
+
+def _to_ncdhw_raw(x: torch.Tensor, Cc: int) -> torch.Tensor:
+    x = x.contiguous()
+    B, T, H, W, Cp = x.shape
+    out = torch.empty((B, Cc, T, H, W), dtype=torch.float32, device=x.device)
+    L.check(L.load().dp_ndhwc_to_ncdhw_f32(x.data_ptr(), out.data_ptr(), B, Cc, Cp, T, H, W, _code(x), L.stream_ptr()),
+            "dp_ndhwc_to_ncdhw_f32")
+    return out
+
+
+class _ToInternal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.c = x.shape[1]
+        return _to_internal_raw(x, dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        return _to_ncdhw_raw(g, ctx.c), None
+
+
+class _ToNCDHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.dtype = x.dtype
+        return _to_ncdhw_raw(x, c)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        return _to_internal_raw(g, ctx.dtype), None
+
+
+def to_internal(x: torch.Tensor) -> torch.Tensor:
+    """NCDHW fp32 (B,C,T,H,W) -> tagged internal NDHWC tensor."""
+    c = x.shape[1]
+    return tag(_ToInternal.apply(x, _STATE["dtype"]), c)
+
+
+def to_ncdhw(x: torch.Tensor) -> torch.Tensor:
+    return _ToNCDHW.apply(x, x._dp_c)
+
+
+def frames_u8_to_internal(frames: torch.Tensor, mean_bgr: Sequence[float]) -> torch.Tensor:
+    """(B,T,H,W,3) uint8 BGR frames -> internal tensor, minus per-channel mean
+    (reference: DatasetForVideo.normalize/to_tensor, /root/reference/src/dataset.py:104-110,201-205)."""
+    L.require_device()
+    if frames.dtype != torch.uint8 or frames.dim() != 5 or frames.shape[-1] != 3 or not frames.is_cuda:
+        raise L.DpError("expected CUDA uint8 frames of shape (B,T,H,W,3)")
+    frames = frames.contiguous()
+    B, T, H, W, _ = frames.shape
+    dtype = _STATE["dtype"]
+    out = torch.empty((B, T, H, W, 16), dtype=dtype, device=frames.device)
+    m = (C.c_float * 3)(*[float(v) for v in mean_bgr])
+    code = L.DP_BF16 if dtype == torch.bfloat16 else L.DP_F32
+    L.check(L.load().dp_u8_frames_to_ndhwc(frames.data_ptr(), out.data_ptr(), m, B, T, H, W, 16, code, L.stream_ptr()),
+            "dp_u8_frames_to_ndhwc")
+    return tag(out, 3)
+
+
+# ----------------------------------------------------------------------------------------------
+# one layer: conv -> BN -> LeakyReLU [-> +residual -> LeakyReLU]
+# ----------------------------------------------------------------------------------------------
+class LayerCfg:
+    """Static description of one Conv3dBlock (reference R2Plus1D.py:25-58)."""
+    __slots__ = ("C", "K", "kernel", "stride", "padding", "slope", "eps", "momentum")
+
+    def __init__(self, C_in, K, kernel, stride, padding, slope, eps=1e-5, momentum=0.1):
+        self.C, self.K = int(C_in), int(K)
+        self.kernel, self.stride, self.padding = tuple(kernel), tuple(stride), tuple(padding)
+        self.slope, self.eps, self.momentum = float(slope), float(eps), float(momentum)
+
+
+class PackedWeights:
+    """Private packed copies of one fp32 master weight, refreshed when the master changes."""
+    __slots__ = ("version", "ptr", "dtype", "wf", "wd")
+
+    def __init__(self):
+        self.version = -1
+        self.ptr = 0
+        self.dtype = None
+        self.wf = None
+        self.wd = None
+
+
+def pack_weights(weight: torch.Tensor, geom: ConvGeom, dtype: torch.dtype, cache: Optional[PackedWeights]):
+    if cache is not None and cache.version == weight._version and cache.ptr == weight.data_ptr() and cache.dtype == dtype:
+        return cache.wf, cache.wd
+    d = geom.desc
+    if weight.dtype != torch.float32 or not weight.is_contiguous():
+        raise L.DpError("conv master weights must be contiguous float32")
+    wf = torch.empty((d.Kp, geom.taps, d.Cp), dtype=dtype, device=weight.device)
+    wd = torch.empty((d.Cp, geom.taps, d.Kp), dtype=dtype, device=weight.device)
+    L.check(L.load().dp_pack_weights(C.byref(d), weight.data_ptr(), wf.data_ptr(), wd.data_ptr(), L.stream_ptr()),
+            "dp_pack_weights")
+    if cache is not None:
+        cache.version, cache.ptr, cache.dtype, cache.wf, cache.wd = weight._version, weight.data_ptr(), dtype, wf, wd
+    return wf, wd
+
+
+def layer_forward(x, weight, gamma, beta, running_mean, running_var, cfg: LayerCfg, training: bool,
+                  residual=None, slope_res: float = 1.0, cache: Optional[PackedWeights] = None):
+    """Returns (z, saved) with saved = (x, y, out_or_None, stats[4,Kp], w_dgrad, geom)."""
+    lib = L.load()
+    st = L.stream_ptr()
+    geom = conv_geom(cfg.C, cfg.K, cfg.kernel, cfg.stride, cfg.padding, x)
+    d = geom.desc
+    wf, wd = pack_weights(weight, geom, x.dtype, cache)
+    dev = x.device
+    y = torch.empty(geom.out_shape, dtype=x.dtype, device=dev)
+    stats = torch.empty((4, d.Kp), dtype=torch.float32, device=dev)  # mean, rstd, scale, shift
+    impl = _STATE["impl"]
+    if training:
+        part = torch.empty((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=dev)
+        nparts = C.c_int(0)
+        L.check(lib.dp_conv_fwd(C.byref(d), x.data_ptr(), wf.data_ptr(), y.data_ptr(), part.data_ptr(),
+                                C.byref(nparts), impl, st), "dp_conv_fwd")
+        L.check(lib.dp_bn_finalize(part.data_ptr(), nparts.value, d.K, d.Kp, float(geom.rows_out), gamma.data_ptr(),
+                                   beta.data_ptr(), cfg.eps, cfg.momentum, _p(running_mean), _p(running_var),
+                                   stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
+                                   st), "dp_bn_finalize")
+    else:
+        L.check(lib.dp_conv_fwd(C.byref(d), x.data_ptr(), wf.data_ptr(), y.data_ptr(), None, None, impl, st),
+                "dp_conv_fwd")
+        if running_mean is None or running_var is None:
+            raise L.DpError("eval-mode BatchNorm needs running statistics")
+        stats.zero_()
+        stats[0, :d.K] = running_mean
+        stats[1, :d.K] = torch.rsqrt(running_var + cfg.eps)
+        L.check(lib.dp_bn_eval_coeffs(running_mean.data_ptr(), running_var.data_ptr(), gamma.data_ptr(),
+                                      beta.data_ptr(), cfg.eps, d.K, d.Kp, stats[2].data_ptr(), stats[3].data_ptr(),
+                                      st), "dp_bn_eval_coeffs")
+    z = torch.empty_like(y)
+    if residual is not None and (residual.shape != y.shape or residual.dtype != y.dtype):
+        raise L.DpError(f"residual {tuple(residual.shape)} {residual.dtype} does not match {tuple(y.shape)} {y.dtype}")
+    L.check(lib.dp_bn_act_apply(y.data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(), cfg.slope, _p(residual),
+                                float(slope_res), z.data_ptr(), geom.rows_out, d.Kp, d.dtype, st), "dp_bn_act_apply")
+    return z, (x, y, z if residual is not None else None, stats, wd, geom)
+
+
+def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope_res: float, need_dx: bool,
+                   addend=None, want_dres: bool = False):
+    """Returns (dx, dw, dgamma, dbeta, dres)."""
+    lib = L.load()
+    st = L.stream_ptr()
+    x, y, out, stats, wd, geom = saved
+    d = geom.desc
+    dev = y.device
+    dz = dz.contiguous()
+    if dz.dtype != y.dtype or dz.shape != y.shape:
+        raise L.DpError(f"grad {tuple(dz.shape)} {dz.dtype} does not match activation {tuple(y.shape)} {y.dtype}")
+    part = torch.empty((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=dev)
+    nparts = C.c_int(0)
+    mean, rstd, scale, shift = (stats[i].data_ptr() for i in range(4))
+    L.check(lib.dp_bn_act_bwd_reduce(dz.data_ptr(), y.data_ptr(), _p(out), scale, shift, mean, rstd, cfg.slope,
+                                     float(slope_res), part.data_ptr(), C.byref(nparts), geom.rows_out, d.Kp, d.dtype,
+                                     st), "dp_bn_act_bwd_reduce")
+    dgamma = torch.empty(d.K, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(d.K, dtype=torch.float32, device=dev)
+    coef = torch.empty((2, d.Kp), dtype=torch.float32, device=dev)
+    L.check(lib.dp_bn_bwd_finalize(part.data_ptr(), nparts.value, d.K, d.Kp, float(geom.rows_out), dgamma.data_ptr(),
+                                   dbeta.data_ptr(), coef.data_ptr(), st), "dp_bn_bwd_finalize")
+    if not training:
+        coef.zero_()  # eval-mode BN: statistics are constants, no mean/variance terms
+    dy = torch.empty_like(y)
+    dres = torch.empty_like(y) if (want_dres and out is not None) else None
+    L.check(lib.dp_bn_act_bwd_apply(dz.data_ptr(), y.data_ptr(), _p(out), scale, shift, mean, rstd, coef.data_ptr(),
+                                    cfg.slope, float(slope_res), dy.data_ptr(), _p(dres), geom.rows_out, d.Kp,
+                                    d.dtype, st), "dp_bn_act_bwd_apply")
+    impl = _STATE["impl"]
+    dw = torch.empty(weight_shape, dtype=torch.float32, device=dev)
+    if geom.ws_bytes is None:
+        geom.ws_bytes = int(lib.dp_conv_wgrad_workspace(C.byref(d), impl))
+    ws = _workspace(geom.ws_bytes, dev)
+    L.check(lib.dp_conv_wgrad(C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(), impl,
+                              st), "dp_conv_wgrad")
+    dx = None
+    if need_dx:
+        dx = torch.empty_like(x)
+        if addend is not None:
+            addend = addend.contiguous()
+            if addend.shape != x.shape or addend.dtype != x.dtype:
+                raise L.DpError("dgrad addend does not match the input activation")
+        L.check(lib.dp_conv_dgrad(C.byref(d), dy.data_ptr(), wd.data_ptr(), _p(addend), dx.data_ptr(), impl, st),
+                "dp_conv_dgrad")
+    elif addend is not None:
+        dx = addend
+    return dx, dw, dgamma, dbeta, dres
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd wrappers
+# ----------------------------------------------------------------------------------------------
+class ConvBnActFn(torch.autograd.Function):
+    """One Conv3dBlock.  inputs: x, weight, gamma, beta, (mod = the nn.Module holding buffers/cfg)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, mod):
+        training = mod.training
+        rm, rv = (mod.bn.running_mean, mod.bn.running_var) if mod.bn.track_running_stats else (None, None)
+        if not training and rm is None:
+            training = True
+        z, saved = layer_forward(x, weight, gamma, beta, rm, rv, mod._cfg, training, cache=mod._packed)
+        xs, y, _, stats, wd, geom = saved
+        ctx.save_for_backward(xs, y, stats, wd)
+        ctx.geom, ctx.cfg, ctx.training, ctx.wshape = geom, mod._cfg, training, weight.shape
+        return z
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dz):
+        xs, y, stats, wd = ctx.saved_tensors
+        dx, dw, dg, db, _ = layer_backward((xs, y, None, stats, wd, ctx.geom), dz, ctx.wshape, ctx.cfg, ctx.training,
+                                           1.0, ctx.needs_input_grad[0])
+        return dx, dw, dg, db, None
+
+
+class AddActFn(torch.autograd.Function):
+    """out = lrelu(a + b, slope): the residual tail of SpatioTemporalResBlock (R2Plus1D.py:187)
+    when the block runs module by module (hooks registered on inner modules)."""
+
+    @staticmethod
+    def forward(ctx, a, b, slope):
+        lib = L.load()
+        Cp = a.shape[-1]
+        ident = torch.zeros((2, Cp), dtype=torch.float32, device=a.device)
+        ident[0].fill_(1.0)
+        out = torch.empty_like(a)
+        rows = a.numel() // Cp
+        L.check(lib.dp_bn_act_apply(a.data_ptr(), ident[0].data_ptr(), ident[1].data_ptr(), 1.0, b.data_ptr(),
+                                    float(slope), out.data_ptr(), rows, Cp, _code(a), L.stream_ptr()), "dp_bn_act_apply")
+        ctx.save_for_backward(out)
+        ctx.slope = float(slope)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        lib = L.load()
+        g = g.contiguous()
+        Cp = out.shape[-1]
+        rows = out.numel() // Cp
+        ident = torch.zeros((6, Cp), dtype=torch.float32, device=out.device)
+        ident[0].fill_(1.0)  # scale=1; shift, mean, rstd, coef0, coef1 = 0
+        d = torch.empty_like(out)
+        dres = torch.empty_like(out)
+        # y := out (any tensor; with rstd=0, coef=0 and slope=1 only the residual derivative acts)
+        L.check(lib.dp_bn_act_bwd_apply(g.data_ptr(), out.data_ptr(), out.data_ptr(), ident[0].data_ptr(),
+                                        ident[1].data_ptr(), ident[2].data_ptr(), ident[3].data_ptr(),
+                                        ident[4].data_ptr(), 1.0, ctx.slope, d.data_ptr(), dres.data_ptr(), rows, Cp,
+                                        _code(out), L.stream_ptr()), "dp_bn_act_bwd_apply")
+        return d, dres, None
+
+
+class ResBlockFn(torch.autograd.Function):
+    """A whole SpatioTemporalResBlock (R2Plus1D.py:164-187) with a hand-ordered backward:
+    the shortcut gradient enters conv1's dgrad as its epilogue addend, so no stand-alone
+    gradient-sum pass exists.  inputs: x, block module, then (weight, gamma, beta) per layer in the
+    order conv1.spatio, conv1.temporal, conv2.spatio, conv2.temporal[, ds.spatio, ds.temporal]."""
+
+    @staticmethod
+    def forward(ctx, x, block, *params):
+        layers = block._dp_layers()
+        training = block.training
+        saved_all = []
+        metas = []
+
+        def run(i, inp, residual=None, slope_res=1.0):
+            m = layers[i]
+            w, g, b = params[3 * i:3 * i + 3]
+            z, saved = layer_forward(inp, w, g, b, m.bn.running_mean, m.bn.running_var, m._cfg, training,
+                                     residual=residual, slope_res=slope_res, cache=m._packed)
+            xs, y, out, stats, wd, geom = saved
+            saved_all.extend([xs, y, stats, wd])
+            metas.append((geom, m._cfg, w.shape))
+            return z
+
+        h = run(0, x)
+        h = run(1, h)
+        h = run(2, h)
+        if block.downsample:
+            sc = run(4, x)   # metas index 3 = ds.spatio, 4 = ds.temporal (kept in call order)
+            sc = run(5, sc)
+        else:
+            sc = x
+        out = run(3, h, residual=sc, slope_res=block.relu.negative_slope)
+        ctx.save_for_backward(out, *saved_all)
+        ctx.metas, ctx.training, ctx.downsample = metas, training, block.downsample
+        ctx.slope_res = float(block.relu.negative_slope)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        t = ctx.saved_tensors
+        out = t[0]
+        sv = [t[1 + 4 * i:1 + 4 * i + 4] for i in range(len(ctx.metas))]
+        # call order in forward: 0 c1.s, 1 c1.t, 2 c2.s, [3 ds.s, 4 ds.t], last = c2.t
+        last = len(ctx.metas) - 1
+
+        def bwd(slot, dz, need_dx=True, addend=None, with_out=False, want_dres=False):
+            xs, y, stats, wd = sv[slot]
+            geom, cfg, wshape = ctx.metas[slot]
+            return layer_backward((xs, y, out if with_out else None, stats, wd, geom), dz, wshape, cfg, ctx.training,
+                                  ctx.slope_res, need_dx, addend=addend, want_dres=want_dres)
+
+        grads = {}
+        d, dw, dg, db, dres = bwd(last, dout, with_out=True, want_dres=True)
+        grads[3] = (dw, dg, db)
+        d, dw, dg, db, _ = bwd(2, d)
+        grads[2] = (dw, dg, db)
+        d, dw, dg, db, _ = bwd(1, d)
+        grads[1] = (dw, dg, db)
+        need_dx = ctx.needs_input_grad[0]
+        if ctx.downsample:
+            ds, dw, dg, db, _ = bwd(4, dres)
+            grads[5] = (dw, dg, db)
+            ds, dw, dg, db, _ = bwd(3, ds, need_dx=need_dx)
+            grads[4] = (dw, dg, db)
+            dx, dw, dg, db, _ = bwd(0, d, need_dx=need_dx, addend=ds)
+        else:
+            dx, dw, dg, db, _ = bwd(0, d, need_dx=need_dx, addend=dres)
+        grads[0] = (dw, dg, db)
+        flat = []
+        for i in range(len(ctx.metas)):
+            flat.extend(grads[i])
+        return (dx, None, *flat)
+
+
+class AvgPoolFn(torch.autograd.Function):
+    """AdaptiveAvgPool3d(1) + view (R2Plus1D.py:215,224-225): internal (B,T,H,W,Cp) -> (B,C) fp32."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        B = x.shape[0]
+        Cp = x.shape[-1]
+        pixels = x.numel() // (B * Cp)
+        out = torch.empty((B, c), dtype=torch.float32, device=x.device)
+        L.check(L.load().dp_avgpool_fwd(x.data_ptr(), out.data_ptr(), B, pixels, c, Cp, _code(x), L.stream_ptr()),
+                "dp_avgpool_fwd")
+        ctx.shape, ctx.dtype, ctx.c = x.shape, x.dtype, c
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        g = g.contiguous().float()
+        B, Cp = ctx.shape[0], ctx.shape[-1]
+        dx = torch.empty(ctx.shape, dtype=ctx.dtype, device=g.device)
+        pixels = dx.numel() // (B * Cp)
+        code = L.DP_BF16 if ctx.dtype == torch.bfloat16 else L.DP_F32
+        L.check(L.load().dp_avgpool_bwd(g.data_ptr(), dx.data_ptr(), B, pixels, ctx.c, Cp, code, L.stream_ptr()),
+                "dp_avgpool_bwd")
+        return dx, None
+
+
+# ----------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------
+class LossFn(torch.autograd.Function):
+    """Fused forward+backward of CE / Focal / LDAM (reference src/loss.py:14-81)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, weight, margins, kind, gamma, s):
+        L.require_device()
+        if not logits.is_cuda or logits.dim() != 2:
+            raise L.DpError("loss: logits must be a CUDA tensor of shape (N, num_classes)")
+        lg = logits.contiguous().float()
+        tg = target.contiguous().view(-1)
+        if tg.dtype != torch.int64:
+            tg = tg.long()
+        if tg.device != lg.device:
+            tg = tg.to(lg.device)
+        n, c = lg.shape
+        if tg.numel() != n:
+            raise L.DpError(f"loss: {n} rows of logits but {tg.numel()} targets")
+        dev = lg.device
+        res = torch.empty(2, dtype=torch.float32, device=dev)
+        dlogits = torch.empty_like(lg)
+        lib = L.load()
+        ws = _zeros_ws("loss", int(lib.dp_loss_workspace(n)), dev)
+        L.check(lib.dp_loss_fwd_bwd(kind, lg.data_ptr(), tg.data_ptr(), _p(weight), _p(margins), float(gamma),
+                                    float(s), n, c, res.data_ptr(), dlogits.data_ptr(), ws.data_ptr(), L.stream_ptr()),
+                "dp_loss_fwd_bwd")
+        ctx.save_for_backward(dlogits, res)
+        ctx.in_dtype = logits.dtype
+        return res[0].clone()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        dlogits, res = ctx.saved_tensors
+        g = g.contiguous().float()
+        out = torch.empty_like(dlogits)
+        L.check(L.load().dp_loss_bwd_scale(dlogits.data_ptr(), g.data_ptr(), res.data_ptr(), out.data_ptr(),
+                                           out.numel(), L.stream_ptr()), "dp_loss_bwd_scale")
+        return out.to(ctx.in_dtype), None, None, None, None, None, None

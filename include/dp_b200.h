@@ -1,0 +1,161 @@
+/*
+ * dp_b200.h -- C ABI of the B200-native R(2+1)D hot path.
+ *
+ * One shared library (libdp_b200.so, built from
+ * disruption-prediciton-based-on-multimodal-deep-learning_b200/csrc) exports exactly the symbols declared
+ * here.  Every entry point takes plain device pointers and sizes, enqueues
+ * work on the cudaStream_t passed as `void* stream`, never allocates device
+ * memory, never synchronises, never throws, and returns DP_OK or a negative
+ * DP_ERR_* code (dp_last_error() gives the text for the calling thread).
+ *
+ * The reference (ZINZINBIN/Disruption-Prediciton-based-on-Multimodal-Deep-Learning)
+ * has no FFI layer of its own: its boundary for this path is the nn.Module /
+ * loss protocol.  Each entry point cites the reference lines whose library
+ * calls (ATen / cuDNN) it replaces.  The ctypes binding a maintainer of the
+ * reference would add is shown in INTEGRATION.md.
+ *
+ * Layout contract (internal to the path):
+ *   activations : NDHWC, channel dimension padded with zeros to Cp = ceil16(C)
+ *   dtype       : DP_BF16 (product path, fp32 accumulate) or DP_F32
+ *                 (fp32 validation mode)
+ *   weights     : caller keeps fp32 (K,C,kt,kh,kw) master tensors (state_dict
+ *                 format); dp_pack_weights makes the private packed copies.
+ */
+#ifndef DP_B200_H
+#define DP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DP_OK               0
+#define DP_ERR_SHAPE       -1
+#define DP_ERR_ALIGN       -2
+#define DP_ERR_ARCH        -3
+#define DP_ERR_CUDA        -4
+#define DP_ERR_UNSUPPORTED -5
+
+#define DP_F32  0
+#define DP_BF16 1
+
+/* kernel family selector for the conv entry points */
+#define DP_IMPL_AUTO 0   /* tcgen05 where the shape is covered, else SIMT */
+#define DP_IMPL_SIMT 1   /* CUDA-core implicit GEMM (any shape, both dtypes) */
+#define DP_IMPL_TC   2   /* TMA + tcgen05/TMEM implicit GEMM (bf16 only) */
+
+/* loss kinds: src/loss.py:71 (CE), :14 (Focal), :37 (LDAM) */
+#define DP_LOSS_CE    0
+#define DP_LOSS_FOCAL 1
+#define DP_LOSS_LDAM  2
+
+/* rows of per-CTA BatchNorm partial sums any producer may emit */
+#define DP_MAX_PARTS 592
+
+/* One Conv3d of the path (nn.Conv3d at src/models/R2Plus1D.py:44-51, bias=False,
+ * dilation 1).  Input (B,Ti,Hi,Wi,Cp) -> output (B,To,Ho,Wo,Kp), NDHWC. */
+typedef struct dp_conv_desc {
+  int32_t B, Ti, Hi, Wi, C, Cp;
+  int32_t To, Ho, Wo, K, Kp;
+  int32_t kt, kh, kw;
+  int32_t st, sh, sw;
+  int32_t pt, ph, pw;
+  int32_t dtype; /* DP_F32 | DP_BF16: storage type of x, y, packed weights */
+} dp_conv_desc;
+
+int         dp_version(void);
+const char* dp_last_error(void);
+/* DP_OK iff the current device is compute capability 10.x (sm_100a code). */
+int         dp_device_check(void);
+int         dp_num_sms(void);
+/* tuning / debug switches: "tc_enable", "tc_halo", "tc_strided", "tc_max_stages" */
+int         dp_set_option(const char* name, int value);
+int         dp_get_option(const char* name);
+
+/* ---- layout (replaces the implicit NCDHW contract of DatasetForVideo, src/dataset.py:229-230) ---- */
+int dp_ncdhw_f32_to_ndhwc(const float* src, void* dst, int B, int C, int Cp, int T, int H, int W,
+                          int dtype, void* stream);
+int dp_ndhwc_to_ncdhw_f32(const void* src, float* dst, int B, int C, int Cp, int T, int H, int W,
+                          int dtype, void* stream);
+/* uint8 frames (B,T,H,W,3) BGR -> mean-subtracted NDHWC (src/dataset.py:104-110,201-205) */
+int dp_u8_frames_to_ndhwc(const uint8_t* src, void* dst, const float* mean3, int B, int T, int H, int W,
+                          int Cp, int dtype, void* stream);
+
+/* ---- weights ---- */
+/* w: fp32 (K,C,kt,kh,kw).  w_fwd: [Kp][taps][Cp], w_dgrad: [Cp][taps][Kp] in desc->dtype. */
+int dp_pack_weights(const dp_conv_desc* d, const float* w, void* w_fwd, void* w_dgrad, void* stream);
+
+/* ---- convolution: forward / dgrad / wgrad (replace cuDNN behind nn.Conv3d, R2Plus1D.py:44-51,57) ---- */
+int dp_conv_supported(const dp_conv_desc* d, int op /*0 fwd,1 dgrad,2 wgrad*/, int impl);
+/* y = conv(x, w).  If `part` is non-NULL, per-channel (sum, sumsq) partials of y
+ * are written to part[nparts][2][Kp] and *nparts is set (<= DP_MAX_PARTS). */
+int dp_conv_fwd(const dp_conv_desc* d, const void* x, const void* w_fwd, void* y,
+                float* part, int* nparts, int impl, void* stream);
+/* dx = conv_transpose(dy, w) (+ addend if non-NULL, same shape as dx). */
+int dp_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend,
+                  void* dx, int impl, void* stream);
+size_t dp_conv_wgrad_workspace(const dp_conv_desc* d, int impl);
+/* dw (fp32, (K,C,kt,kh,kw)) = x^T * dy, deterministic split reduction through `workspace`. */
+int dp_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw,
+                  void* workspace, size_t workspace_bytes, int impl, void* stream);
+
+/* ---- BatchNorm3d (train) + LeakyReLU (R2Plus1D.py:53-57,179-187) ---- */
+int dp_bn_stats(const void* y, int64_t rows, int Cp, int dtype, float* part, int* nparts, void* stream);
+int dp_bn_finalize(const float* part, int nparts, int C, int Cp, double count,
+                   const float* gamma, const float* beta, float eps, float momentum,
+                   float* running_mean, float* running_var,
+                   float* mean, float* rstd, float* scale, float* shift, void* stream);
+int dp_bn_eval_coeffs(const float* running_mean, const float* running_var, const float* gamma,
+                      const float* beta, float eps, int C, int Cp, float* scale, float* shift,
+                      void* stream);
+/* z = lrelu(y*scale+shift, slope); if residual: z = lrelu(z + residual, slope_res). */
+int dp_bn_act_apply(const void* y, const float* scale, const float* shift, float slope,
+                    const void* residual, float slope_res, void* z, int64_t rows, int Cp,
+                    int dtype, void* stream);
+/* backward of the above, pass 1: per-channel sum(g), sum(g*xhat) partials. */
+int dp_bn_act_bwd_reduce(const void* dz, const void* y, const void* out,
+                         const float* scale, const float* shift, const float* mean,
+                         const float* rstd, float slope, float slope_res,
+                         float* part, int* nparts, int64_t rows, int Cp, int dtype, void* stream);
+int dp_bn_bwd_finalize(const float* part, int nparts, int C, int Cp, double count,
+                       float* dgamma, float* dbeta, float* coef, void* stream);
+/* pass 2: dy = scale*(g - coef0 - xhat*coef1); optionally dres = dz*lrelu'(out). */
+int dp_bn_act_bwd_apply(const void* dz, const void* y, const void* out,
+                        const float* scale, const float* shift, const float* mean,
+                        const float* rstd, const float* coef, float slope, float slope_res,
+                        void* dy, void* dres, int64_t rows, int Cp, int dtype, void* stream);
+/* plain elementwise sum of two activation tensors (grad fan-in at block inputs) */
+int dp_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+
+/* ---- AdaptiveAvgPool3d(1) (R2Plus1D.py:215,224-225) ---- */
+int dp_avgpool_fwd(const void* x, float* out, int B, int64_t pixels, int C, int Cp, int dtype,
+                   void* stream);
+int dp_avgpool_bwd(const float* dout, void* dx, int B, int64_t pixels, int C, int Cp, int dtype,
+                   void* stream);
+
+/* ---- losses (src/loss.py:14-81) ---- */
+size_t dp_loss_workspace(int64_t n);
+/* loss_out[0] = loss, loss_out[1] = normaliser (sum w[y] for LDAM, 1 otherwise).
+ * dlogits = d(loss * normaliser)/dlogits, i.e. unnormalised. */
+int dp_loss_fwd_bwd(int kind, const float* logits, const int64_t* target, const float* weight,
+                    const float* margins, float gamma, float s, int64_t n, int C,
+                    float* loss_out, float* dlogits, void* workspace, void* stream);
+/* out = dlogits * grad_out[0] / loss_out[1]  (device scalars, no host sync) */
+int dp_loss_bwd_scale(const float* dlogits, const float* grad_out, const float* loss_out,
+                      float* out, int64_t count, void* stream);
+
+/* ---- fused optimiser tail (src/train.py:63-66: clip_grad_norm_ + AdamW.step) ---- */
+size_t dp_optim_workspace(int64_t n);
+/* flat fp32 param/grad/moment buffers of n elements; decoupled weight decay (AdamW).
+ * max_norm <= 0 disables clipping.  grad_scale multiplies g first (1/world for DP mean). */
+int dp_clip_adamw_step(float* p, const float* g, float* m, float* v, int64_t n,
+                       float lr, float beta1, float beta2, float eps, float weight_decay,
+                       int step, float max_norm, float grad_scale, float* norm_out,
+                       void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DP_B200_H */

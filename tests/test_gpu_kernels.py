@@ -1,0 +1,355 @@
+"""Kernel-level parity on the GPU, every call through the C ABI (ctypes): each CUDA kernel against a
+plain PyTorch fp32 restatement of the same op on the same seeded inputs.
+
+Tolerances: fp32 validation kernels 1e-4 relative (north_star); bf16 kernels compare against the fp32
+op evaluated on the SAME bf16-rounded operands, so only accumulation order and the final bf16 rounding
+of the output differ: 2^-8 relative to the tensor's scale."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import dp_b200
+from dp_b200 import _lib as L
+from dp_b200 import functional as Fn
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def to_int(x, dtype):
+    """NCDHW fp32 -> internal via the kernel."""
+    return Fn._to_internal_raw(x.contiguous(), dtype)
+
+
+def from_int(x, c):
+    return Fn._to_ncdhw_raw(x, c)
+
+
+# ---- R(2+1)D [1,2,2,1] layer geometries at T=21,128^2 scaled to a small clip ------------
+# (C, K, kernel, stride, padding, T, H, W)
+GEOMS = [
+    (3, 45, (1, 7, 7), (1, 2, 2), (0, 3, 3), 5, 32, 32),      # stem spatial
+    (45, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), 5, 16, 16),     # stem temporal
+    (32, 72, (1, 3, 3), (1, 1, 1), (0, 1, 1), 5, 16, 16),     # conv2 spatial
+    (72, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), 5, 16, 16),     # conv2 temporal
+    (32, 115, (1, 3, 3), (1, 2, 2), (0, 1, 1), 5, 16, 16),    # conv3 down spatial
+    (115, 64, (3, 1, 1), (2, 1, 1), (1, 0, 0), 5, 8, 8),      # conv3 down temporal
+    (64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), 3, 8, 8),      # conv3/4 spatial
+    (144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 3, 8, 8),      # conv3/4 temporal
+    (32, 21, (1, 1, 1), (1, 2, 2), (0, 0, 0), 5, 16, 16),     # shortcut spatial
+    (21, 64, (1, 1, 1), (2, 1, 1), (0, 0, 0), 5, 8, 8),       # shortcut temporal
+    (64, 230, (1, 3, 3), (1, 2, 2), (0, 1, 1), 3, 8, 8),      # conv5 down spatial
+    (230, 128, (3, 1, 1), (2, 1, 1), (1, 0, 0), 3, 4, 4),     # conv5 down temporal
+    (128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 4, 4),     # conv5 spatial (N > 256)
+    (288, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0), 2, 4, 4),     # conv5 temporal
+]
+# full-resolution shapes for the tensor-core family (tile edges, halo boxes, 64-wide rows)
+GEOMS_BIG = [
+    (32, 72, (1, 3, 3), (1, 1, 1), (0, 1, 1), 21, 64, 64),
+    (72, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), 21, 64, 64),
+    (45, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), 21, 64, 64),
+    (64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), 11, 32, 32),
+    (144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 11, 32, 32),
+    (64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), 6, 16, 16),
+    (128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), 3, 8, 8),
+    (288, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0), 3, 8, 8),
+    (3, 45, (1, 7, 7), (1, 2, 2), (0, 3, 3), 21, 128, 128),
+    (32, 115, (1, 3, 3), (1, 2, 2), (0, 1, 1), 21, 64, 64),
+    (115, 64, (3, 1, 1), (2, 1, 1), (1, 0, 0), 21, 32, 32),
+    (32, 21, (1, 1, 1), (1, 2, 2), (0, 0, 0), 21, 64, 64),
+    (21, 64, (1, 1, 1), (2, 1, 1), (0, 0, 0), 21, 32, 32),
+]
+
+
+def make_case(geom, B, dtype, seed=0):
+    Cc, K, k, s, p, T, H, W = geom
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cc, T, H, W, generator=g)
+    w = torch.randn(K, Cc, *k, generator=g) * math.sqrt(2.0 / (Cc * k[0] * k[1] * k[2]))
+    if dtype == torch.bfloat16:  # compare on identical (bf16-representable) operands
+        x = x.bfloat16().float()
+        w = w.bfloat16().float()
+    return x.to(DEV), w.to(DEV)
+
+
+def run_conv(geom, B, dtype, impl, x, w, dy=None, addend=None):
+    """Returns y (NCDHW fp32) and, if dy given, (dx, dw)."""
+    Cc, K, k, s, p, T, H, W = geom
+    lib = L.load()
+    xi = to_int(x, dtype)
+    gm = Fn.conv_geom(Cc, K, k, s, p, xi)
+    d = gm.desc
+    wf, wd = Fn.pack_weights(w.contiguous(), gm, dtype, None)
+    y = torch.empty(gm.out_shape, dtype=dtype, device=DEV)
+    part = torch.zeros((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=DEV)
+    nparts = C.c_int(0)
+    L.check(lib.dp_conv_fwd(C.byref(d), xi.data_ptr(), wf.data_ptr(), y.data_ptr(), part.data_ptr(), C.byref(nparts),
+                            impl, L.stream_ptr()), "fwd")
+    out = {"y": from_int(y, K), "y_int": y, "part": part[:nparts.value].clone(), "rows": gm.rows_out, "K": K}
+    if dy is not None:
+        dyi = to_int(dy, dtype)
+        dx = torch.empty_like(xi)
+        ad = to_int(addend, dtype) if addend is not None else None
+        L.check(lib.dp_conv_dgrad(C.byref(d), dyi.data_ptr(), wd.data_ptr(), None if ad is None else ad.data_ptr(),
+                                  dx.data_ptr(), impl, L.stream_ptr()), "dgrad")
+        dw = torch.empty_like(w)
+        nbytes = int(lib.dp_conv_wgrad_workspace(C.byref(d), impl))
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=DEV)
+        L.check(lib.dp_conv_wgrad(C.byref(d), xi.data_ptr(), dyi.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  impl, L.stream_ptr()), "wgrad")
+        out["dx"] = from_int(dx, Cc)
+        out["dw"] = dw
+    return out
+
+
+def torch_ref(geom, x, w, dy=None):
+    Cc, K, k, s, p, T, H, W = geom
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        xr = x.clone().double().requires_grad_(True)   # fp64: an exact-enough reference for both modes
+        wr = w.clone().double().requires_grad_(True)
+        y = F.conv3d(xr, wr, None, s, p)
+        out = {"y": y.detach()}
+        if dy is not None:
+            y.backward(dy.double())
+            out["dx"], out["dw"] = xr.grad, wr.grad
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return out
+
+
+@pytest.mark.parametrize("geom", GEOMS, ids=lambda g: f"{g[0]}to{g[1]}_k{g[2]}_s{g[3]}")
+def test_conv_simt_fp32(geom):
+    B = 2
+    x, w = make_case(geom, B, torch.float32)
+    ref = torch_ref(geom, x, w)
+    dy = torch.randn_like(ref["y"], dtype=torch.float32)
+    ref = torch_ref(geom, x, w, dy)
+    got = run_conv(geom, B, torch.float32, L.IMPL_SIMT, x, w, dy)
+    assert rel_err(got["y"], ref["y"]) < 1e-5
+    assert rel_err(got["dx"], ref["dx"]) < 1e-5
+    assert rel_err(got["dw"], ref["dw"]) < 1e-5
+    # BN partial statistics of the conv output
+    s = got["part"].double().sum(0)
+    yy = ref["y"].double()
+    assert rel_err(s[0, :geom[1]], yy.sum(dim=(0, 2, 3, 4))) < 1e-4
+    assert rel_err(s[1, :geom[1]], (yy * yy).sum(dim=(0, 2, 3, 4))) < 1e-4
+
+
+@pytest.mark.parametrize("geom", GEOMS, ids=lambda g: f"{g[0]}to{g[1]}_k{g[2]}_s{g[3]}")
+def test_conv_simt_bf16(geom):
+    B = 2
+    x, w = make_case(geom, B, torch.bfloat16)
+    ref = torch_ref(geom, x, w)
+    dy = torch.randn_like(ref["y"], dtype=torch.float32).bfloat16().float()
+    ref = torch_ref(geom, x, w, dy)
+    got = run_conv(geom, B, torch.bfloat16, L.IMPL_SIMT, x, w, dy)
+    assert rel_err(got["y"], ref["y"]) < 2 ** -7
+    assert rel_err(got["dx"], ref["dx"]) < 2 ** -7
+    assert rel_err(got["dw"], ref["dw"]) < 1e-4   # fp32 output, fp32 accumulation
+
+
+def _tc_check(geom, B, seed=0):
+    lib = L.load()
+    x, w = make_case(geom, B, torch.bfloat16, seed)
+    ref = torch_ref(geom, x, w)
+    dy = torch.randn_like(ref["y"], dtype=torch.float32).bfloat16().float()
+    ref = torch_ref(geom, x, w, dy)
+    Cc, K, k, s, p, T, H, W = geom
+    xi = to_int(x, torch.bfloat16)
+    gm = Fn.conv_geom(Cc, K, k, s, p, xi)
+    d = gm.desc
+    res = {}
+    if lib.dp_conv_supported(C.byref(d), 0, L.IMPL_TC):
+        wf, wd = Fn.pack_weights(w.contiguous(), gm, torch.bfloat16, None)
+        y = torch.full(gm.out_shape, float("nan"), dtype=torch.bfloat16, device=DEV)
+        part = torch.zeros((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=DEV)
+        nparts = C.c_int(0)
+        L.check(lib.dp_conv_fwd(C.byref(d), xi.data_ptr(), wf.data_ptr(), y.data_ptr(), part.data_ptr(),
+                                C.byref(nparts), L.IMPL_TC, L.stream_ptr()), "tc fwd")
+        torch.cuda.synchronize()
+        yo = from_int(y, K)
+        res["fwd"] = rel_err(yo, ref["y"])
+        assert torch.isfinite(y.float()).all(), "tc fwd left unwritten (NaN) output elements"
+        assert (y[..., K:] == 0).all(), "padded output channels must be exactly zero"
+        st = part[:nparts.value].double().sum(0)
+        yb = yo.double()   # statistics are taken from the bf16-rounded tile
+        res["sum"] = rel_err(st[0, :K], yb.sum(dim=(0, 2, 3, 4)))
+        res["sq"] = rel_err(st[1, :K], (yb * yb).sum(dim=(0, 2, 3, 4)))
+        assert res["fwd"] < 2 ** -7, res
+        assert res["sum"] < 1e-3 and res["sq"] < 1e-3, res
+    if lib.dp_conv_supported(C.byref(d), 1, L.IMPL_TC):
+        wf, wd = Fn.pack_weights(w.contiguous(), gm, torch.bfloat16, None)
+        dyi = to_int(dy, torch.bfloat16)
+        for use_add in (False, True):
+            ad = torch.randn_like(x).bfloat16().float() if use_add else None
+            adi = to_int(ad, torch.bfloat16) if use_add else None
+            dx = torch.full(gm.in_shape, float("nan"), dtype=torch.bfloat16, device=DEV)
+            L.check(lib.dp_conv_dgrad(C.byref(d), dyi.data_ptr(), wd.data_ptr(),
+                                      None if adi is None else adi.data_ptr(), dx.data_ptr(), L.IMPL_TC,
+                                      L.stream_ptr()), "tc dgrad")
+            torch.cuda.synchronize()
+            want = ref["dx"] + (ad.double() if use_add else 0)
+            res["dgrad_add" if use_add else "dgrad"] = rel_err(from_int(dx, Cc), want)
+            assert res["dgrad_add" if use_add else "dgrad"] < 2 ** -7, res
+    if lib.dp_conv_supported(C.byref(d), 2, L.IMPL_TC):
+        dyi = to_int(dy, torch.bfloat16)
+        dw = torch.empty_like(w)
+        nbytes = int(lib.dp_conv_wgrad_workspace(C.byref(d), L.IMPL_TC))
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=DEV)
+        L.check(lib.dp_conv_wgrad(C.byref(d), xi.data_ptr(), dyi.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  L.IMPL_TC, L.stream_ptr()), "tc wgrad")
+        torch.cuda.synchronize()
+        res["wgrad"] = rel_err(dw, ref["dw"])
+        assert res["wgrad"] < 1e-3, res
+    return res
+
+
+@pytest.mark.parametrize("geom", GEOMS + GEOMS_BIG, ids=lambda g: f"{g[0]}to{g[1]}_k{g[2]}_s{g[3]}_{g[5]}x{g[6]}")
+def test_conv_tcgen05(geom):
+    res = _tc_check(geom, B=2)
+    print(geom, res)
+
+
+def test_conv_tcgen05_modes():
+    """Same geometry through the per-tap path and the halo-reuse path must agree with the reference."""
+    try:
+        for halo in (0, 1):
+            L.set_option("tc_halo", halo)
+            for geom in (GEOMS_BIG[0], GEOMS_BIG[1], GEOMS_BIG[3]):
+                _tc_check(geom, B=1, seed=3)
+    finally:
+        L.set_option("tc_halo", 1)
+
+
+# ---- BatchNorm / activation ------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C_", [32, 45, 72, 288])
+def test_bn_act_fwd_bwd(dtype, C_):
+    lib = L.load()
+    g = torch.Generator().manual_seed(1)
+    B, T, H, W = 2, 3, 8, 8
+    slope, slope_res = 0.01, 0.3
+    y = (torch.randn(B, C_, T, H, W, generator=g) * 2 + 0.5)
+    res = torch.randn(B, C_, T, H, W, generator=g)
+    dz = torch.randn(B, C_, T, H, W, generator=g)
+    gamma = torch.rand(C_, generator=g) + 0.5
+    beta = torch.randn(C_, generator=g) * 0.1
+    if dtype == torch.bfloat16:
+        y, res, dz = y.bfloat16().float(), res.bfloat16().float(), dz.bfloat16().float()
+    y, res, dz, gamma, beta = (t.to(DEV) for t in (y, res, dz, gamma, beta))
+    for use_res in (False, True):
+        # reference
+        yr = y.clone().requires_grad_(True)
+        rr = res.clone().requires_grad_(True)
+        gr = gamma.clone().requires_grad_(True)
+        br = beta.clone().requires_grad_(True)
+        rm, rv = torch.zeros(C_, device=DEV), torch.ones(C_, device=DEV)
+        z = F.leaky_relu(F.batch_norm(yr, rm, rv, gr, br, True, 0.1, 1e-5), slope)
+        if use_res:
+            z = F.leaky_relu(z + rr, slope_res)
+        z.backward(dz)
+        # ours
+        Cp = Fn.ceil16(C_)
+        yi, ri, dzi = to_int(y, dtype), to_int(res, dtype), to_int(dz, dtype)
+        rows = B * T * H * W
+        part = torch.zeros((L.DP_MAX_PARTS, 2, Cp), dtype=torch.float32, device=DEV)
+        nparts = C.c_int(0)
+        st_ = L.stream_ptr()
+        L.check(lib.dp_bn_stats(yi.data_ptr(), rows, Cp, Fn._code(yi), part.data_ptr(), C.byref(nparts), st_))
+        stats = torch.zeros((4, Cp), dtype=torch.float32, device=DEV)
+        rm2, rv2 = torch.zeros(C_, device=DEV), torch.ones(C_, device=DEV)
+        L.check(lib.dp_bn_finalize(part.data_ptr(), nparts.value, C_, Cp, float(rows), gamma.data_ptr(), beta.data_ptr(),
+                                   1e-5, 0.1, rm2.data_ptr(), rv2.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                                   stats[2].data_ptr(), stats[3].data_ptr(), st_))
+        zi = torch.empty_like(yi)
+        L.check(lib.dp_bn_act_apply(yi.data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(), slope,
+                                    ri.data_ptr() if use_res else None, slope_res, zi.data_ptr(), rows, Cp,
+                                    Fn._code(yi), st_))
+        tol = 1e-4 if dtype == torch.float32 else 2 ** -7
+        assert rel_err(from_int(zi, C_), z.detach()) < tol
+        assert rel_err(rm2, rm) < 1e-5 and rel_err(rv2, rv) < 1e-5
+        assert (zi[..., C_:] == 0).all()
+        L.check(lib.dp_bn_act_bwd_reduce(dzi.data_ptr(), yi.data_ptr(), zi.data_ptr() if use_res else None,
+                                         stats[2].data_ptr(), stats[3].data_ptr(), stats[0].data_ptr(),
+                                         stats[1].data_ptr(), slope, slope_res, part.data_ptr(), C.byref(nparts), rows,
+                                         Cp, Fn._code(yi), st_))
+        dgamma, dbeta = torch.empty(C_, device=DEV), torch.empty(C_, device=DEV)
+        coef = torch.empty((2, Cp), device=DEV)
+        L.check(lib.dp_bn_bwd_finalize(part.data_ptr(), nparts.value, C_, Cp, float(rows), dgamma.data_ptr(),
+                                       dbeta.data_ptr(), coef.data_ptr(), st_))
+        dyi = torch.empty_like(yi)
+        dres = torch.empty_like(yi) if use_res else None
+        L.check(lib.dp_bn_act_bwd_apply(dzi.data_ptr(), yi.data_ptr(), zi.data_ptr() if use_res else None,
+                                        stats[2].data_ptr(), stats[3].data_ptr(), stats[0].data_ptr(),
+                                        stats[1].data_ptr(), coef.data_ptr(), slope, slope_res, dyi.data_ptr(),
+                                        None if dres is None else dres.data_ptr(), rows, Cp, Fn._code(yi), st_))
+        gtol = 2e-4 if dtype == torch.float32 else 2 ** -6
+        assert rel_err(dgamma, gr.grad) < gtol
+        assert rel_err(dbeta, br.grad) < gtol
+        assert rel_err(from_int(dyi, C_), yr.grad) < gtol
+        if use_res:
+            assert rel_err(from_int(dres, C_), rr.grad) < gtol
+
+
+def test_layout_roundtrip_and_u8():
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 45, 3, 6, 10, generator=g).to(DEV)
+    for dtype in (torch.float32, torch.bfloat16):
+        xi = to_int(x, dtype)
+        assert xi.shape == (2, 3, 6, 10, 48)
+        want = x.permute(0, 2, 3, 4, 1).to(dtype)
+        assert torch.equal(xi[..., :45], want)
+        assert (xi[..., 45:] == 0).all()
+        back = from_int(xi, 45)
+        assert torch.equal(back, want.permute(0, 4, 1, 2, 3).float())
+    frames = torch.randint(0, 256, (2, 3, 8, 8, 3), generator=g, dtype=torch.uint8).to(DEV)
+    with dp_b200.compute_mode("bf16"):
+        xi = Fn.frames_u8_to_internal(frames, (90.0, 98.0, 102.0))
+    want = (frames.float() - torch.tensor([90.0, 98.0, 102.0], device=DEV)).bfloat16()
+    assert torch.equal(xi[..., :3], want) and (xi[..., 3:] == 0).all()
+
+
+def test_avgpool():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 128, 3, 8, 8, generator=g).to(DEV)
+    for dtype in (torch.float32, torch.bfloat16):
+        xi = Fn.tag(to_int(x, dtype), 128).requires_grad_(True)
+        out = Fn.AvgPoolFn.apply(xi, 128)
+        want = xi.detach().float()[..., :128].mean(dim=(1, 2, 3))
+        assert rel_err(out, want) < 1e-5
+        go = torch.randn(3, 128, generator=g).to(DEV)
+        out.backward(go)
+        wantg = (go / 192.0)[:, None, None, None, :].expand(3, 3, 8, 8, 128)
+        assert rel_err(xi.grad.float()[..., :128], wantg.to(dtype).float()) < 1e-6
+
+
+def test_fused_clip_adamw_matches_torch():
+    from dp_b200.optim import FusedClipAdamW
+    g = torch.Generator().manual_seed(4)
+    shapes = [(45, 3, 1, 7, 7), (45,), (32, 45, 3, 1, 1), (7,), (64, 128)]
+    ps_a = [torch.nn.Parameter(torch.randn(s, generator=g).to(DEV)) for s in shapes]
+    ps_b = [torch.nn.Parameter(p.detach().clone()) for p in ps_a]
+    oa = FusedClipAdamW(ps_a, lr=2e-4, max_norm=1.0)
+    ob = torch.optim.AdamW(ps_b, lr=2e-4)
+    for step in range(3):
+        for pa, pb in zip(ps_a, ps_b):
+            gr = torch.randn(pa.shape, generator=g).to(DEV) * (5.0 if step == 0 else 0.01)
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        norm_b = torch.nn.utils.clip_grad_norm_(ps_b, 1.0)
+        ob.step()
+        oa.step()
+        assert rel_err(oa.last_grad_norm[0], norm_b) < 1e-5
+        for pa, pb in zip(ps_a, ps_b):
+            assert rel_err(pa.detach(), pb.detach()) < 1e-5
