@@ -253,7 +253,17 @@ class R2Plus1DClassifier(nn.Module):
     def get_res2plus1d_output_size(self):
         # The reference pushes a zero clip through the encoder on the CPU (:255-259); the pooled width
         # does not depend on the clip, so it is stated instead of executed (no CPU path here).
+        # That probe runs in training mode, so in the reference every BatchNorm3d leaves the constructor
+        # having seen one all-zero batch (bias-free convs of zeros are zeros): running_mean *= (1-momentum),
+        # running_var = (1-momentum)*1 + momentum*0 = 0.9, num_batches_tracked = 1.  Reproduced here so a
+        # freshly constructed model has the reference's buffers bit for bit.
         self._check_input_size()
+        with torch.no_grad():
+            for m in self.res2plus1d.modules():
+                if isinstance(m, nn.BatchNorm3d) and m.track_running_stats and m.momentum is not None:
+                    m.running_mean.mul_(1.0 - m.momentum)
+                    m.running_var.mul_(1.0 - m.momentum)
+                    m.num_batches_tracked.add_(1)
         return torch.Size([1, self.res2plus1d.out_features])
 
     def _check_input_size(self):

@@ -42,6 +42,7 @@ SIGNATURES = {
     "dp_last_error": (C.c_char_p, []),
     "dp_device_check": (_i, []),
     "dp_num_sms": (_i, []),
+    "dp_launch_count": (C.c_ulonglong, []),
     "dp_set_option": (_i, [C.c_char_p, _i]),
     "dp_get_option": (_i, [C.c_char_p]),
     "dp_ncdhw_f32_to_ndhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

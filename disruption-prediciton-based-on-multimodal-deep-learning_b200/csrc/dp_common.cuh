@@ -13,7 +13,10 @@ namespace dp {
 
 void set_error(const char* fmt, ...);
 
+extern unsigned long long g_launches;  // kernels launched by this library (dp_launch_count)
+
 inline int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));

@@ -5,6 +5,7 @@
 namespace dp {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -30,6 +31,8 @@ DP_API int dp_version(void) { return 100; }
 DP_API const char* dp_last_error(void) { return dp::g_err; }
 
 DP_API int dp_num_sms(void) { return dp::num_sms(); }
+
+DP_API unsigned long long dp_launch_count(void) { return dp::g_launches; }
 
 DP_API int dp_device_check(void) {
   int dev = 0;

@@ -49,6 +49,44 @@ def compute_mode(mode: str, impl: Optional[str] = None):
         _STATE.update(old)
 
 
+class KernelProfiler:
+    """CUDA-event timing of each C-ABI kernel call on the launching stream (bench.py's roofline leg).
+    Records (family, algorithmic flops, algorithmic bytes, start event, end event)."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(fam, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+            d["launches"] += 1
+        return out
+
+
+PROFILER: Optional[KernelProfiler] = None
+
+
+def _pb():
+    if PROFILER is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _pe(e0, family, flops=0.0, nbytes=0.0):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    PROFILER.records.append((family, flops, nbytes, e0, e1))
+
+
 def ceil16(c: int) -> int:
     return (c + 15) // 16 * 16
 
@@ -78,7 +116,8 @@ def _p(t: Optional[torch.Tensor]):
 # geometry cache
 # ----------------------------------------------------------------------------------------------
 class ConvGeom:
-    __slots__ = ("desc", "rows_out", "rows_in", "out_shape", "in_shape", "taps", "ws_bytes", "key")
+    __slots__ = ("desc", "rows_out", "rows_in", "out_shape", "in_shape", "taps", "ws_bytes", "key", "flops", "esize",
+                 "fam")
 
     def __init__(self, C_in, K, kernel, stride, padding, B, T, H, W, dtype_code):
         kt, kh, kw = kernel
@@ -97,6 +136,18 @@ class ConvGeom:
         self.in_shape = (B, T, H, W, ceil16(C_in))
         self.taps = kt * kh * kw
         self.ws_bytes = None
+        self.flops = 2.0 * self.rows_out * K * C_in * self.taps      # algorithmic (unpadded) FLOPs of one pass
+        self.esize = 2 if dtype_code == L.DP_BF16 else 4
+        self.fam = None
+
+    def families(self, impl):
+        """Which kernel family serves fwd / dgrad / wgrad for this geometry (profiling labels)."""
+        if self.fam is None or self.fam[0] != impl:
+            lib = L.load()
+            tc = [bool(impl != L.IMPL_SIMT and lib.dp_conv_supported(C.byref(self.desc), op, L.IMPL_TC)) for op in range(3)]
+            self.fam = (impl, "tc_gather_gemm" if tc[0] else "simt_gather_gemm",
+                        "tc_gather_gemm" if tc[1] else "simt_gather_gemm", "tc_wgrad" if tc[2] else "simt_wgrad")
+        return self.fam
 
 
 _GEOMS = {}
@@ -268,8 +319,11 @@ def layer_forward(x, weight, gamma, beta, running_mean, running_var, cfg: LayerC
     if training:
         part = torch.empty((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=dev)
         nparts = C.c_int(0)
+        t0 = _pb()
         L.check(lib.dp_conv_fwd(C.byref(d), x.data_ptr(), wf.data_ptr(), y.data_ptr(), part.data_ptr(),
                                 C.byref(nparts), impl, st), "dp_conv_fwd")
+        if t0 is not None:
+            _pe(t0, geom.families(impl)[1], geom.flops, geom.esize * (geom.rows_in * d.C + geom.rows_out * d.K))
         L.check(lib.dp_bn_finalize(part.data_ptr(), nparts.value, d.K, d.Kp, float(geom.rows_out), gamma.data_ptr(),
                                    beta.data_ptr(), cfg.eps, cfg.momentum, _p(running_mean), _p(running_var),
                                    stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
@@ -288,8 +342,11 @@ def layer_forward(x, weight, gamma, beta, running_mean, running_var, cfg: LayerC
     z = torch.empty_like(y)
     if residual is not None and (residual.shape != y.shape or residual.dtype != y.dtype):
         raise L.DpError(f"residual {tuple(residual.shape)} {residual.dtype} does not match {tuple(y.shape)} {y.dtype}")
+    t0 = _pb()
     L.check(lib.dp_bn_act_apply(y.data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(), cfg.slope, _p(residual),
                                 float(slope_res), z.data_ptr(), geom.rows_out, d.Kp, d.dtype, st), "dp_bn_act_apply")
+    if t0 is not None:
+        _pe(t0, "bn_act_apply", 0.0, geom.esize * geom.rows_out * d.K * (3 if residual is not None else 2))
     return z, (x, y, z if residual is not None else None, stats, wd, geom)
 
 
@@ -307,9 +364,13 @@ def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope
     part = torch.empty((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=dev)
     nparts = C.c_int(0)
     mean, rstd, scale, shift = (stats[i].data_ptr() for i in range(4))
+    elems = geom.esize * geom.rows_out * d.K
+    t0 = _pb()
     L.check(lib.dp_bn_act_bwd_reduce(dz.data_ptr(), y.data_ptr(), _p(out), scale, shift, mean, rstd, cfg.slope,
                                      float(slope_res), part.data_ptr(), C.byref(nparts), geom.rows_out, d.Kp, d.dtype,
                                      st), "dp_bn_act_bwd_reduce")
+    if t0 is not None:
+        _pe(t0, "bn_act_bwd_reduce", 0.0, elems * (3 if out is not None else 2))
     dgamma = torch.empty(d.K, dtype=torch.float32, device=dev)
     dbeta = torch.empty(d.K, dtype=torch.float32, device=dev)
     coef = torch.empty((2, d.Kp), dtype=torch.float32, device=dev)
@@ -319,16 +380,23 @@ def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope
         coef.zero_()  # eval-mode BN: statistics are constants, no mean/variance terms
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if (want_dres and out is not None) else None
+    t0 = _pb()
     L.check(lib.dp_bn_act_bwd_apply(dz.data_ptr(), y.data_ptr(), _p(out), scale, shift, mean, rstd, coef.data_ptr(),
                                     cfg.slope, float(slope_res), dy.data_ptr(), _p(dres), geom.rows_out, d.Kp,
                                     d.dtype, st), "dp_bn_act_bwd_apply")
+    if t0 is not None:
+        _pe(t0, "bn_act_bwd_apply", 0.0, elems * (3 + (1 if out is not None else 0) + (1 if dres is not None else 0)))
     impl = _STATE["impl"]
     dw = torch.empty(weight_shape, dtype=torch.float32, device=dev)
     if geom.ws_bytes is None:
         geom.ws_bytes = int(lib.dp_conv_wgrad_workspace(C.byref(d), impl))
     ws = _workspace(geom.ws_bytes, dev)
+    io_bytes = geom.esize * (geom.rows_in * d.C + geom.rows_out * d.K)
+    t0 = _pb()
     L.check(lib.dp_conv_wgrad(C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(), impl,
                               st), "dp_conv_wgrad")
+    if t0 is not None:
+        _pe(t0, geom.families(impl)[3], geom.flops, io_bytes)
     dx = None
     if need_dx:
         dx = torch.empty_like(x)
@@ -336,8 +404,11 @@ def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope
             addend = addend.contiguous()
             if addend.shape != x.shape or addend.dtype != x.dtype:
                 raise L.DpError("dgrad addend does not match the input activation")
+        t0 = _pb()
         L.check(lib.dp_conv_dgrad(C.byref(d), dy.data_ptr(), wd.data_ptr(), _p(addend), dx.data_ptr(), impl, st),
                 "dp_conv_dgrad")
+        if t0 is not None:
+            _pe(t0, geom.families(impl)[2], geom.flops, io_bytes)
     elif addend is not None:
         dx = addend
     return dx, dw, dgamma, dbeta, dres

@@ -115,10 +115,12 @@ def init_state(layer_sizes: Sequence[int], num_classes: int = 2, seed: Optional[
     return st
 
 
-def clone_state(state: Dict[str, torch.Tensor], requires_grad: bool = True) -> Dict[str, torch.Tensor]:
+def clone_state(state: Dict[str, torch.Tensor], requires_grad: bool = True, dtype=None) -> Dict[str, torch.Tensor]:
     out = {}
     for k, v in state.items():
         t = v.detach().clone().cpu()
+        if dtype is not None and t.is_floating_point():
+            t = t.to(dtype)
         if requires_grad and t.is_floating_point() and "running_" not in k:
             t.requires_grad_(True)
         out[k] = t
@@ -126,38 +128,84 @@ def clone_state(state: Dict[str, torch.Tensor], requires_grad: bool = True) -> D
 
 
 # ----------------------------------------------------------------------------------------------
+# bf16-storage emulation
+# ----------------------------------------------------------------------------------------------
+# storage="bf16" restates the SAME fp32 algorithm but rounds tensors to bfloat16 at exactly the
+# points where the CUDA product path stores them in HBM (conv input, packed weights, raw conv output,
+# post-activation output, and the gradients of those tensors on the way back).  It answers "what does
+# the reference's algorithm give when activations live in bf16", which is the fair checker for the bf16
+# kernels: bf16 storage alone moves logits by several percent on noise inputs (numerics).
+class _RoundBoth(torch.autograd.Function):
+    """Round to bf16 in forward (stored activation) and in backward (stored gradient)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().to(g.dtype)
+
+
+class _RoundFwd(torch.autograd.Function):
+    """Round to bf16 in forward only (packed weights; weight gradients stay fp32)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _q(x, storage):
+    return _RoundBoth.apply(x) if storage == "bf16" else x
+
+
+# ----------------------------------------------------------------------------------------------
 # forward
 # ----------------------------------------------------------------------------------------------
-def conv_bn_act(st, name, x, kernel, stride, padding, slope, training, taps=None):
+def conv_bn_act(st, name, x, kernel, stride, padding, slope, training, taps=None, storage="fp32", round_out=True):
     """Conv3dBlock.forward: LeakyReLU(BN3d(Conv3d(x)))   (R2Plus1D.py:56-58)."""
-    y = F.conv3d(x, st[name + ".conv.weight"], None, stride, padding)
+    w = st[name + ".conv.weight"]
+    if storage == "bf16":
+        w = _RoundFwd.apply(w)
+    y = _q(F.conv3d(x, w, None, stride, padding), storage)
     rm, rv = st[name + ".bn.running_mean"], st[name + ".bn.running_var"]
     z = F.batch_norm(y, rm, rv, st[name + ".bn.weight"], st[name + ".bn.bias"], training, BN_MOMENTUM, BN_EPS)
     if training:
         st[name + ".bn.num_batches_tracked"] += 1
     out = F.leaky_relu(z, slope)
+    if round_out:
+        out = _q(out, storage)
     if taps is not None:
         taps[name + ".conv"] = y
         taps[name] = out
     return out
 
 
-def st_conv(st, layers, x, training, taps=None):
-    for (name, _, _, k, s, p, slope) in layers:
-        x = conv_bn_act(st, name, x, k, s, p, slope, training, taps)
+def st_conv(st, layers, x, training, taps=None, storage="fp32", round_last=True):
+    for i, (name, _, _, k, s, p, slope) in enumerate(layers):
+        x = conv_bn_act(st, name, x, k, s, p, slope, training, taps, storage,
+                        round_out=round_last or i + 1 < len(layers))
     return x
 
 
-def encoder_forward(st, x, layer_sizes, alpha, training=True, taps=None):
+def encoder_forward(st, x, layer_sizes, alpha, training=True, taps=None, storage="fp32"):
     """R2Plus1DNet.forward (R2Plus1D.py:217-226): x (B,3,T,H,W) fp32 -> (B,128)."""
     stem, blocks = encoder_plan(layer_sizes, alpha)
-    x = st_conv(st, stem, x, training, taps)
+    x = _q(x, storage)
+    x = st_conv(st, stem, x, training, taps, storage)
     for b in blocks:
-        res = st_conv(st, b["conv1"], x, training, taps)
-        res = st_conv(st, b["conv2"], res, training, taps)
+        res = st_conv(st, b["conv1"], x, training, taps, storage)
+        # the CUDA path keeps conv2's activation in registers and stores only lrelu(shortcut + res)
+        res = st_conv(st, b["conv2"], res, training, taps, storage, round_last=False)
         if b["shortcut"] is not None:
-            x = st_conv(st, b["shortcut"], x, training, taps)
-        x = F.leaky_relu(x + res, b["slope"])
+            sc = st_conv(st, b["shortcut"], _q(x, storage), training, taps, storage)
+        else:
+            sc = _q(x, storage)
+        x = _q(F.leaky_relu(sc + res, b["slope"]), storage)
         if taps is not None:
             taps[b["prefix"]] = x
     x = F.adaptive_avg_pool3d(x, 1)
@@ -175,8 +223,8 @@ def head_forward(st, feat, alpha, training=True):
     return F.linear(h, st["linear.3.weight"], st["linear.3.bias"])
 
 
-def classifier_forward(st, x, layer_sizes, alpha, training=True, taps=None):
-    return head_forward(st, encoder_forward(st, x, layer_sizes, alpha, training, taps), alpha, training)
+def classifier_forward(st, x, layer_sizes, alpha, training=True, taps=None, storage="fp32"):
+    return head_forward(st, encoder_forward(st, x, layer_sizes, alpha, training, taps, storage), alpha, training)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -249,9 +297,42 @@ def synthetic_clips(B: int, T: int = 21, H: int = 128, W: int = 128, seed: int =
     return x, y
 
 
-def train_step(st, x, y, layer_sizes, alpha, loss="focal", weight=None, margins=None, gamma=2.0, s=30.0):
+def structured_clips(B: int, T: int = 21, H: int = 128, W: int = 128, seed: int = 1234, noise: int = 6):
+    """Camera-like synthetic clips: a dark background with a few bright, slowly moving Gaussian blobs whose
+    position / size / brightness / colour differ from clip to clip, plus +-`noise` grey levels of sensor noise,
+    quantised to uint8 and mean-subtracted exactly like `synthetic_clips`.  IVIS frames are of this kind (a
+    bright plasma boundary on a dark vessel); unlike i.i.d. pixel noise, the clips of a batch differ
+    macroscopically, so the batch statistics of the head's BatchNorm1d are well conditioned."""
+    g = torch.Generator().manual_seed(seed)
+    yy = torch.linspace(0, 1, H).view(1, 1, H, 1)
+    xx = torch.linspace(0, 1, W).view(1, 1, 1, W)
+    tt = torch.arange(T, dtype=torch.float32).view(1, T, 1, 1)
+    clips = torch.zeros(B, 3, T, H, W)
+    for b in range(B):
+        img = torch.rand(1, generator=g).item() * 55.0 + 5.0 + torch.zeros(3, T, H, W)
+        for _ in range(4):
+            cx, cy = (torch.rand(2, generator=g) * 0.6 + 0.2).tolist()
+            vx, vy = ((torch.rand(2, generator=g) - 0.5) * 0.02).tolist()
+            sig = torch.rand(1, generator=g).item() * 0.2 + 0.05
+            amp = torch.rand(1, generator=g).item() * 180.0 + 40.0
+            gain = torch.rand(3, generator=g) * 0.4 + 0.6
+            flick = 1.0 + 0.1 * torch.sin(tt * (torch.rand(1, generator=g).item() * 0.8 + 0.1))
+            r2 = (xx - (cx + vx * tt)) ** 2 + (yy - (cy + vy * tt)) ** 2
+            blob = amp * flick * torch.exp(-r2 / (2 * sig * sig))          # (1,T,H,W)
+            img = img + gain.view(3, 1, 1, 1) * blob
+        clips[b] = img
+    if noise > 0:
+        clips += torch.randint(-noise, noise + 1, clips.shape, generator=g).float()
+    x = clips.round().clamp_(0, 255)
+    x -= torch.tensor([90.0, 98.0, 102.0]).view(1, 3, 1, 1, 1)
+    y = torch.randint(0, 2, (B,), generator=g)
+    return x, y
+
+
+def train_step(st, x, y, layer_sizes, alpha, loss="focal", weight=None, margins=None, gamma=2.0, s=30.0,
+               storage="fp32"):
     """One forward + loss + backward on the port; returns (logits, loss, {name: grad})."""
-    logits = classifier_forward(st, x, layer_sizes, alpha, training=True)
+    logits = classifier_forward(st, x, layer_sizes, alpha, training=True, storage=storage)
     if weight is None:
         weight = torch.ones(logits.shape[1])
     if loss == "focal":

@@ -1,0 +1,161 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dp_b200.h declares (no compute calls), the
+ctypes prototypes agree with the header, the drop-in modules keep the reference's surface, and the
+product path fails loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import dp_b200
+from dp_b200 import _lib, distributed as dpd, inference
+from dp_b200.R2Plus1D import Conv3dBlock, R2Plus1DClassifier, SpatioTemporalConv, SpatioTemporalResBlock
+from dp_b200.loss import CELoss, FocalLoss, ImbalancedDatasetSampler, LDAMLoss
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "dp_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    # "<ret> dp_xxx(" at the start of a declaration
+    return sorted(set(re.findall(r"\b(dp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "libdp_b200.so must be built in-tree (python -c 'import __graft_entry__ as g; g.build()')"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/dp_b200.h but not exported"
+    # and the Python binding table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_header_argument_counts_match_binding():
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert n == len(args), (name, n, len(args))
+
+
+def test_host_only_entry_points():
+    lib = _lib.load()
+    assert lib.dp_version() >= 100
+    assert lib.dp_launch_count() == 0
+    assert _lib.get_option("tc_enable") in (0, 1)
+    with pytest.raises(_lib.DpError):
+        _lib.set_option("no_such_option", 1)
+    # struct layout mirrors dp_conv_desc: 21 int32
+    assert ctypes.sizeof(_lib.ConvDesc) == 21 * 4
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    m = R2Plus1DClassifier((3, 5, 32, 32), 2, [1, 1, 1, 1], False, 0.01)
+    with pytest.raises(_lib.DpError):
+        m(torch.zeros(2, 3, 5, 32, 32))
+    with pytest.raises(_lib.DpError):
+        FocalLoss(weight=torch.ones(2))(torch.zeros(4, 2), torch.zeros(4, dtype=torch.long))
+    with pytest.raises(_lib.DpError):
+        _lib.require_device()
+
+
+def test_module_surface_matches_reference():
+    """State-dict keys, shapes, attribute names and constructor defaults the reference's callers rely on
+    (SURVEY.md section 8b)."""
+    m = R2Plus1DClassifier((3, 21, 128, 128), 2, [1, 2, 2, 1], False, 1.0)
+    sd = m.state_dict()
+    assert len(sd) == 201
+    assert sd["res2plus1d.conv1.spatio_conv.conv.weight"].shape == (45, 3, 1, 7, 7)
+    assert sd["res2plus1d.conv1.temporal_conv.conv.weight"].shape == (32, 45, 3, 1, 1)
+    assert sd["res2plus1d.conv3.block1.downsample_conv.spatio_conv.conv.weight"].shape == (21, 32, 1, 1, 1)
+    assert sd["res2plus1d.conv5.block1.conv2.spatio_conv.conv.weight"].shape == (288, 128, 1, 3, 3)
+    assert "res2plus1d.conv2.block1.conv1.spatio_conv.bn.num_batches_tracked" in sd
+    assert sd["linear.3.weight"].shape == (2, 64)
+    assert m.input_size == (3, 21, 128, 128)
+    for name in ("conv1", "conv2", "conv3", "conv4", "conv5", "pool"):
+        assert hasattr(m.res2plus1d, name)
+    mids = [m.res2plus1d.conv2.block1.conv1.spatio_conv.conv.out_channels,
+            m.res2plus1d.conv3.block1.conv1.spatio_conv.conv.out_channels,
+            m.res2plus1d.conv3.block1.conv2.spatio_conv.conv.out_channels,
+            m.res2plus1d.conv5.block1.conv1.spatio_conv.conv.out_channels,
+            m.res2plus1d.conv5.block1.conv2.spatio_conv.conv.out_channels,
+            m.res2plus1d.conv3.block1.downsample_conv.spatio_conv.conv.out_channels,
+            m.res2plus1d.conv5.block1.downsample_conv.spatio_conv.conv.out_channels]
+    assert mids == [72, 115, 144, 230, 288, 21, 42]
+    # inner activations use the SpatioTemporalConv default slope, block end / stem use alpha (R2Plus1D.py:172-179,210)
+    assert m.res2plus1d.conv2.block1.conv1.spatio_conv.relu.negative_slope == 0.01
+    assert m.res2plus1d.conv2.block1.relu.negative_slope == 1.0
+    assert m.res2plus1d.conv1.spatio_conv.relu.negative_slope == 1.0
+    # int kernel / stride / padding promotion (R2Plus1D.py:29-42)
+    b = Conv3dBlock(4, 8, 3, 2, 1, 1)
+    assert b.conv.kernel_size == (1, 3, 3) and b.conv.stride == (1, 2, 2) and b.conv.padding == (0, 1, 1)
+    s = SpatioTemporalConv(32, 64, (3, 3, 3), (2, 2, 2), 1, (1, 1, 1))
+    assert s.spatio_conv.conv.out_channels == 115 and s.temporal_conv.conv.stride == (2, 1, 1)
+    r = SpatioTemporalResBlock(32, 64, 3, downsample=True)
+    assert r.downsample_conv.spatio_conv.conv.kernel_size == (1, 1, 1)
+    with pytest.raises(NotImplementedError):
+        Conv3dBlock(4, 8, 3, 1, 2, 1)
+    # the optimiser / clip / checkpoint protocol sees ordinary fp32 parameters
+    assert all(p.dtype == torch.float32 for p in m.parameters())
+    m2 = R2Plus1DClassifier((3, 21, 128, 128), 2, [1, 2, 2, 1], False, 1.0)
+    m2.load_state_dict(sd)
+    with pytest.raises(ValueError):
+        R2Plus1DClassifier((3, 21, 4, 4), 2, [1, 1, 1, 1])._check_input_size() or R2Plus1DClassifier((1, 21, 64, 64))
+
+
+def test_loss_surface():
+    f = FocalLoss(weight=torch.ones(2), gamma=2.0)
+    l = LDAMLoss([300, 17000], max_m=0.5, weight=None, s=30)
+    c = CELoss()
+    assert (f.model_type, l.model_type, c.model_type) == ("Focal", "LDAM", "CE")
+    np.testing.assert_allclose(l.m_list.numpy(), 0.5 * np.array([1.0, (300 / 17000) ** 0.25]), rtol=1e-6)
+    for lf in (f, l, c):
+        lf.update_weight(torch.tensor([0.3, 0.7]))
+        assert torch.equal(lf.weight, torch.tensor([0.3, 0.7]))
+    l.update_m_list([10, 1000])
+    assert abs(l.m_list[0].item() - 0.5) < 1e-7
+    with pytest.raises(AssertionError):
+        FocalLoss(gamma=-1.0)
+
+
+def test_imbalanced_sampler_rebalances():
+    class DS:
+        labels = [0] * 20 + [1] * 980
+
+        def __len__(self):
+            return len(self.labels)
+
+    torch.manual_seed(0)
+    s = ImbalancedDatasetSampler(DS())
+    assert len(s) == 1000
+    idx = list(iter(s))
+    frac0 = sum(1 for i in idx if DS.labels[i] == 0) / len(idx)
+    assert 0.42 < frac0 < 0.58          # 1/count weights => classes drawn about equally
+    assert abs(s.weights[:20].sum().item() - 1.0) < 1e-9 and abs(s.weights[20:].sum().item() - 1.0) < 1e-9
+
+
+def test_shards_and_windows():
+    for n, w in ((1000, 8), (984, 4), (7, 8), (0, 2)):
+        covered = []
+        for r in range(w):
+            covered += list(dpd.shard_range(n, r, w))
+        assert covered == list(range(n))
+    assert inference.num_windows(1024, 21, 3) == 1000
+    assert inference.num_windows(10, 21, 3) == 0
+    curve = inference.postprocess_curve([0.9, 0.9, 0.2, 0.7, 0.1], clip_len=2, frame_srt=1, fps=4)
+    assert curve == [0, 0, 0, 0, 0.2, 0.7]                  # start-up suppression below fps frames
+    m = R2Plus1DClassifier((3, 21, 128, 128), 2, [1, 2, 2, 1], False, 1.0)
+    buckets = dpd.stage_buckets(m)
+    assert len(buckets) == 6
+    assert sum(p.numel() for b in buckets for p in b) == 1_587_523
+    assert buckets[0][0] is m.linear[0].weight               # head first: its gradient is ready first
