@@ -289,8 +289,18 @@ class PackedWeights:
         self.wd = None
 
 
+_WEIGHT_EPOCH = [0]
+
+
+def bump_weight_epoch() -> None:
+    """Called by code that updates master weights through raw pointers (the fused optimiser kernel), which
+    autograd's version counter cannot see: every packed copy is rebuilt at its next use."""
+    _WEIGHT_EPOCH[0] += 1
+
+
 def pack_weights(weight: torch.Tensor, geom: ConvGeom, dtype: torch.dtype, cache: Optional[PackedWeights]):
-    if cache is not None and cache.version == weight._version and cache.ptr == weight.data_ptr() and cache.dtype == dtype:
+    version = (weight._version, _WEIGHT_EPOCH[0])
+    if cache is not None and cache.version == version and cache.ptr == weight.data_ptr() and cache.dtype == dtype:
         return cache.wf, cache.wd
     d = geom.desc
     if weight.dtype != torch.float32 or not weight.is_contiguous():
@@ -300,7 +310,7 @@ def pack_weights(weight: torch.Tensor, geom: ConvGeom, dtype: torch.dtype, cache
     L.check(L.load().dp_pack_weights(C.byref(d), weight.data_ptr(), wf.data_ptr(), wd.data_ptr(), L.stream_ptr()),
             "dp_pack_weights")
     if cache is not None:
-        cache.version, cache.ptr, cache.dtype, cache.wf, cache.wd = weight._version, weight.data_ptr(), dtype, wf, wd
+        cache.version, cache.ptr, cache.dtype, cache.wf, cache.wd = version, weight.data_ptr(), dtype, wf, wd
     return wf, wd
 
 

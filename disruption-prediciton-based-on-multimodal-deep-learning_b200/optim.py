@@ -14,6 +14,7 @@ from typing import Iterable, Optional
 import torch
 
 from . import _lib as L
+from . import functional as Fn
 
 
 class FusedClipAdamW(torch.optim.Optimizer):
@@ -92,4 +93,5 @@ class FusedClipAdamW(torch.optim.Optimizer):
                                            float(mn) if mn else 0.0, float(self.grad_scale), st["norm"].data_ptr(),
                                            st["ws"].data_ptr(), L.stream_ptr()), "dp_clip_adamw_step")
             self.last_grad_norm = st["norm"]
+        Fn.bump_weight_epoch()   # the kernel wrote the master weights through raw pointers
         return loss
