@@ -11,6 +11,11 @@ int simt_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const 
 int simt_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw, void* ws,
                     cudaStream_t s);
 size_t simt_wgrad_workspace(const dp_conv_desc* d);
+// dw (K,C,taps) = sum over splits of partial[split][Kp][taps][Cp], fixed order
+int wgrad_reduce_launch(const float* partial, float* dw, int nsplit, int K, int C, int Kp, int Cp, int taps,
+                        cudaStream_t s);
+int wg_option(const char* name, int value, bool set);
+int tc_option(const char* name, int value, bool set);
 
 // tcgen05 family (conv_tc.cu / wgrad_tc.cu)
 bool tc_fwd_supported(const dp_conv_desc* d);

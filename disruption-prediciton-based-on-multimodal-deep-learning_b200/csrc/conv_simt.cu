@@ -177,18 +177,35 @@ wgrad_kernel(Geom g, const T* __restrict__ x, const T* __restrict__ dy, float* _
   }
 }
 
-// dw[k][c][tap] (PyTorch (K,C,kt,kh,kw) order) = sum_split partial[split][k][tap][c]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
-                                    int nsplit, int K, int C, int Kp, int Cp, int taps) {
+// dw[k][c][tap] (PyTorch (K,C,kt,kh,kw) order) = sum_split partial[split][k][tap][c], splits added in a fixed
+// order (deterministic).  Threads run along c, so every split's read is a coalesced row.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                    int nsplit, int K, int C, int Kp, int Cp, int taps) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = K * C * taps;
+  const int total = K * taps * Cp;
   if (idx >= total) return;
-  const int tap = idx % taps, c = (idx / taps) % C, k = idx / (taps * C);
+  const int c = idx % Cp, tap = (idx / Cp) % taps, k = idx / (Cp * taps);
+  if (c >= C) return;
   const int64_t stride = (int64_t)Kp * taps * Cp;
-  const float* p = partial + ((int64_t)k * taps + tap) * Cp + c;
-  float s = 0.f;
-  for (int i = 0; i < nsplit; ++i) s += p[i * stride];
-  dw[idx] = s;
+  const float* p = partial + idx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int i = 0;
+  for (; i + 4 <= nsplit; i += 4) {
+    s0 += p[(int64_t)i * stride];
+    s1 += p[(int64_t)(i + 1) * stride];
+    s2 += p[(int64_t)(i + 2) * stride];
+    s3 += p[(int64_t)(i + 3) * stride];
+  }
+  for (; i < nsplit; ++i) s0 += p[(int64_t)i * stride];
+  dw[((int64_t)k * C + c) * taps + tap] = (s0 + s1) + (s2 + s3);
+}
+
+int wgrad_reduce_launch(const float* partial, float* dw, int nsplit, int K, int C, int Kp, int Cp, int taps,
+                        cudaStream_t s) {
+  const int total = K * taps * Cp;
+  wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, s>>>(partial, dw, nsplit, K, C, Kp, Cp, taps);
+  return check_launch("conv_wgrad_reduce");
 }
 
 static Geom fwd_geom(const dp_conv_desc* d) {
@@ -262,9 +279,7 @@ static int launch_wgrad(const dp_conv_desc* d, const void* x, const void* dy, fl
   wgrad_kernel<T><<<grid, 256, 0, s>>>(g, (const T*)x, (const T*)dy, (float*)ws, M, ch, ctiles);
   int rc = check_launch("conv_wgrad_simt");
   if (rc != DP_OK) return rc;
-  const int total = d->K * d->C * taps;
-  wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, s>>>((const float*)ws, dw, ns, d->K, d->C, d->Kp, d->Cp, taps);
-  return check_launch("conv_wgrad_reduce");
+  return wgrad_reduce_launch((const float*)ws, dw, ns, d->K, d->C, d->Kp, d->Cp, taps, s);
 }
 
 int simt_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s) {

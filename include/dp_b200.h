@@ -72,7 +72,7 @@ int         dp_device_check(void);
 int         dp_num_sms(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long dp_launch_count(void);
-/* tuning / debug switches: "tc_enable", "tc_halo", "tc_strided", "tc_max_stages" */
+/* tuning / debug switches: "tc_enable", "tc_halo", "tc_strided", "tc_max_stages", "wg_enable", "wg_halo" */
 int         dp_set_option(const char* name, int value);
 int         dp_get_option(const char* name);
 

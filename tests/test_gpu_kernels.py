@@ -220,6 +220,7 @@ def _tc_check(geom, B, seed=0):
 def test_conv_tcgen05(geom):
     res = _tc_check(geom, B=2)
     print(geom, res)
+    assert "fwd" in res and "wgrad" in res, "every geometry of the path has a tcgen05 forward and weight-gradient kernel"
 
 
 def test_conv_tcgen05_modes():
@@ -227,10 +228,12 @@ def test_conv_tcgen05_modes():
     try:
         for halo in (0, 1):
             L.set_option("tc_halo", halo)
+            L.set_option("wg_halo", halo)
             for geom in (GEOMS_BIG[0], GEOMS_BIG[1], GEOMS_BIG[3]):
                 _tc_check(geom, B=1, seed=3)
     finally:
         L.set_option("tc_halo", 1)
+        L.set_option("wg_halo", 1)
 
 
 # ---- BatchNorm / activation ------------------------------------------------------------------------
