@@ -43,6 +43,7 @@ struct TcParams {
   int off_staging, off_stats, off_scratch, off_bars;
   int tmem_cols, layout_type, sbo_bytes;
   int has_stats, has_addend;
+  long long a_off, a_sw, a_sh, a_st, a_sb;  // addend view: element offset / strides of (w,h,t,b) in the dst tensor
   signed char off_w[TC_MAX_LOADS], off_h[TC_MAX_LOADS], off_t[TC_MAX_LOADS];
   short tap0[TC_MAX_LOADS];
 };
@@ -172,7 +173,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const bool valid = (w < p.dW) && (h < p.dH) && (t < p.dT);
       const __nv_bfloat16* arow = nullptr;
       if (p.has_addend && valid)
-        arow = addend + ((((int64_t)b * p.dT + t) * p.dH + h) * p.dW + w) * p.dC + n_idx * p.Ntile;
+        arow = addend + p.a_off + (int64_t)b * p.a_sb + (int64_t)t * p.a_st + (int64_t)h * p.a_sh + (int64_t)w * p.a_sw +
+               n_idx * p.Ntile;
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -293,11 +295,16 @@ int tc_option(const char* name, int value, bool set) {
 struct GatherProblem {
   int B;
   int sT, sH, sW, sC;
-  int dT, dH, dW, dC;
-  int kt, kh, kw;
+  int dT, dH, dW, dC;   // destination VIEW dims (what the kernel tiles over)
+  int kt, kh, kw;       // tap positions visited per dim
+  int Kt, Kh, Kw;       // full kernel dims (weight layout [N][Kt*Kh*Kw][C])
   int mt, mh, mw;
-  int ot, oh, ow;  // source coordinate offset of tap position j = 0
-  bool flip;       // weight tap for position j is (k-1-j)
+  int ot, oh, ow;       // source coordinate offset of tap position j = 0 (position j reads offset o + j)
+  int ts_t, ts_h, ts_w; // weight tap used by position j is ts + tp * j
+  int tp_t, tp_h, tp_w;
+  // destination view inside the full tensor (FT,FH,FW): origin and step per dim (strided dgrad parity classes)
+  int FT, FH, FW;
+  int vo_t, vo_h, vo_w, vs_t, vs_h, vs_w;
 };
 
 struct TcPlan {
@@ -313,7 +320,7 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
   if (!g_opt_tc) return false;
   const int taps = g.kt * g.kh * g.kw;
-  if (taps > TC_MAX_LOADS) return false;
+  if (taps > TC_MAX_LOADS || taps < 1) return false;
   if (g.sC % 16 || g.dC % 16) return false;
   const bool strided = (g.mt != 1 || g.mh != 1 || g.mw != 1);
   if (strided && !g_opt_strided) return false;
@@ -386,8 +393,8 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
   out->a_estride[0] = 1; out->a_estride[1] = g.mw; out->a_estride[2] = g.mh; out->a_estride[3] = g.mt; out->a_estride[4] = 1;
   out->a_box[0] = p.CB; out->a_box[4] = 1;
   auto tap_index = [&](int jt, int jh, int jw) {
-    if (g.flip) { jt = g.kt - 1 - jt; jh = g.kh - 1 - jh; jw = g.kw - 1 - jw; }
-    return (jt * g.kh + jh) * g.kw + jw;
+    jt = g.ts_t + g.tp_t * jt; jh = g.ts_h + g.tp_h * jh; jw = g.ts_w + g.tp_w * jw;
+    return (jt * g.Kh + jh) * g.Kw + jw;
   };
   if (best_mode == 0) {
     p.nloads = taps; p.nsub = 1; p.sub_row_bytes = 0; p.tap_sub_stride = 0;
@@ -456,6 +463,22 @@ static int encode_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, 
   return DP_OK;
 }
 
+// destination view: explicit element strides (strided-dgrad parity classes write every s-th pixel)
+static int encode_view_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, long long sw_, long long sh_,
+                           long long st_, long long sb_, const int* box) {
+  PFN_encodeTiled enc = get_encode();
+  DP_REQUIRE(enc != nullptr, DP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)sw_ * 2, (cuuint64_t)sh_ * 2, (cuuint64_t)st_ * 2, (cuuint64_t)sb_ * 2};
+  cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 5; ++i) b[i] = (cuuint32_t)box[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, b, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DP_REQUIRE(r == CUDA_SUCCESS, DP_ERR_CUDA, "cuTensorMapEncodeTiled(destination view) failed: CUresult %d", (int)r);
+  return DP_OK;
+}
+
 static int encode_wgt_map(CUtensorMap* m, const void* ptr, int Ktot, int rows, int boxK, int boxN,
                           CUtensorMapSwizzle sw) {
   PFN_encodeTiled enc = get_encode();
@@ -484,12 +507,17 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   CUtensorMap tmA, tmB, tmD;
   int rc = encode_act_map(&tmA, src, g.sC, g.sW, g.sH, g.sT, g.B, plan.a_box, plan.a_estride, sw);
   if (rc != DP_OK) return rc;
-  const int taps = g.kt * g.kh * g.kw;
+  const int taps = g.Kt * g.Kh * g.Kw;
   rc = encode_wgt_map(&tmB, wgt, taps * g.sC, g.dC, p.CB, p.Ntile, sw);
   if (rc != DP_OK) return rc;
   const int dbox[5] = {p.Ntile, p.bw, p.bh, p.bt, 1};
-  const int ones[5] = {1, 1, 1, 1, 1};
-  rc = encode_act_map(&tmD, dst, g.dC, g.dW, g.dH, g.dT, g.B, dbox, ones, CU_TENSOR_MAP_SWIZZLE_NONE);
+  p.a_sw = (long long)g.vs_w * g.dC;
+  p.a_sh = (long long)g.vs_h * g.FW * g.dC;
+  p.a_st = (long long)g.vs_t * g.FH * g.FW * g.dC;
+  p.a_sb = (long long)g.FT * g.FH * g.FW * g.dC;
+  p.a_off = (((long long)g.vo_t * g.FH + g.vo_h) * g.FW + g.vo_w) * g.dC;
+  rc = encode_view_map(&tmD, (const __nv_bfloat16*)dst + p.a_off, g.dC, g.dW, g.dH, g.dT, g.B, p.a_sw, p.a_sh, p.a_st,
+                       p.a_sb, dbox);
   if (rc != DP_OK) return rc;
 
   static std::once_flag attr_once;
@@ -511,21 +539,47 @@ static GatherProblem fwd_problem(const dp_conv_desc* d) {
   g.dT = d->To; g.dH = d->Ho; g.dW = d->Wo; g.dC = d->Kp;
   g.kt = d->kt; g.kh = d->kh; g.kw = d->kw;
   g.mt = d->st; g.mh = d->sh; g.mw = d->sw;
+  g.Kt = d->kt; g.Kh = d->kh; g.Kw = d->kw;
   g.ot = -d->pt; g.oh = -d->ph; g.ow = -d->pw;
-  g.flip = false;
+  g.ts_t = g.ts_h = g.ts_w = 0;
+  g.tp_t = g.tp_h = g.tp_w = 1;
+  g.FT = g.dT; g.FH = g.dH; g.FW = g.dW;
+  g.vo_t = g.vo_h = g.vo_w = 0;
+  g.vs_t = g.vs_h = g.vs_w = 1;
   return g;
 }
 
-static bool dgrad_problem(const dp_conv_desc* d, GatherProblem* g) {
-  if (d->st != 1 || d->sh != 1 || d->sw != 1) return false;
-  if (d->To != d->Ti || d->Ho != d->Hi || d->Wo != d->Wi) return false;
+// One parity class (rt,rh,rw) of the data gradient: input pixels p = s*q + r receive
+//   dx[p] = sum over taps j with (r + pad - j) % s == 0 of  dy[q + (r + pad - j)/s] * w[j],
+// a stride-1 gather over dy with a strided subset of the taps, written to every s-th pixel of dx.
+// Returns false when the class has no pixel; *ntaps == 0 when it has pixels but no contributing tap.
+static bool dgrad_class(const dp_conv_desc* d, int rt, int rh, int rw, GatherProblem* g, int* ntaps) {
+  const int in[3] = {d->Ti, d->Hi, d->Wi}, out[3] = {d->To, d->Ho, d->Wo};
+  const int k[3] = {d->kt, d->kh, d->kw}, st[3] = {d->st, d->sh, d->sw}, pad[3] = {d->pt, d->ph, d->pw};
+  const int r[3] = {rt, rh, rw};
+  int cnt[3], j0[3], off0[3], vd[3];
+  for (int i = 0; i < 3; ++i) {
+    if (r[i] >= in[i]) return false;
+    vd[i] = (in[i] - r[i] + st[i] - 1) / st[i];
+    j0[i] = (r[i] + pad[i]) % st[i];
+    cnt[i] = j0[i] < k[i] ? (k[i] - 1 - j0[i]) / st[i] + 1 : 0;
+    // position q = cnt-1-i  <->  tap j0 + s*i, source offset (r + pad - j0)/s - i
+    off0[i] = (r[i] + pad[i] - j0[i]) / st[i] - (cnt[i] - 1);
+  }
+  (void)out;
   g->B = d->B;
   g->sT = d->To; g->sH = d->Ho; g->sW = d->Wo; g->sC = d->Kp;
-  g->dT = d->Ti; g->dH = d->Hi; g->dW = d->Wi; g->dC = d->Cp;
-  g->kt = d->kt; g->kh = d->kh; g->kw = d->kw;
+  g->dT = vd[0]; g->dH = vd[1]; g->dW = vd[2]; g->dC = d->Cp;
+  g->kt = cnt[0]; g->kh = cnt[1]; g->kw = cnt[2];
+  g->Kt = d->kt; g->Kh = d->kh; g->Kw = d->kw;
   g->mt = g->mh = g->mw = 1;
-  g->ot = d->pt - (d->kt - 1); g->oh = d->ph - (d->kh - 1); g->ow = d->pw - (d->kw - 1);
-  g->flip = true;
+  g->ot = off0[0]; g->oh = off0[1]; g->ow = off0[2];
+  g->ts_t = j0[0] + st[0] * (cnt[0] - 1); g->ts_h = j0[1] + st[1] * (cnt[1] - 1); g->ts_w = j0[2] + st[2] * (cnt[2] - 1);
+  g->tp_t = -st[0]; g->tp_h = -st[1]; g->tp_w = -st[2];
+  g->FT = d->Ti; g->FH = d->Hi; g->FW = d->Wi;
+  g->vo_t = rt; g->vo_h = rh; g->vo_w = rw;
+  g->vs_t = st[0]; g->vs_h = st[1]; g->vs_w = st[2];
+  *ntaps = cnt[0] * cnt[1] * cnt[2];
   return true;
 }
 
@@ -537,10 +591,19 @@ bool tc_fwd_supported(const dp_conv_desc* d) {
 
 bool tc_dgrad_supported(const dp_conv_desc* d) {
   if (d->dtype != DP_BF16) return false;
-  GatherProblem g;
-  if (!dgrad_problem(d, &g)) return false;
-  TcPlan plan;
-  return plan_gather(g, false, &plan);
+  const bool strided = d->st != 1 || d->sh != 1 || d->sw != 1;
+  if (strided && !g_opt_strided) return false;
+  if (d->st > 4 || d->sh > 4 || d->sw > 4) return false;
+  for (int rt = 0; rt < d->st; ++rt)
+    for (int rh = 0; rh < d->sh; ++rh)
+      for (int rw = 0; rw < d->sw; ++rw) {
+        GatherProblem g;
+        int ntaps = 0;
+        if (!dgrad_class(d, rt, rh, rw, &g, &ntaps) || ntaps == 0) continue;
+        TcPlan plan;
+        if (!plan_gather(g, false, &plan)) return false;
+      }
+  return true;
 }
 
 int tc_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, float* part, int* nparts,
@@ -550,9 +613,31 @@ int tc_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, fl
 
 int tc_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
                   cudaStream_t s) {
-  GatherProblem g;
-  DP_REQUIRE(dgrad_problem(d, &g), DP_ERR_UNSUPPORTED, "tcgen05 dgrad: strided geometry not supported");
-  return launch_gather(g, dy, w, dx, addend, nullptr, nullptr, s);
+  // pixels of classes without a contributing tap (1x1x1 strided shortcuts) receive the addend or zero
+  bool any_empty = false;
+  for (int rt = 0; rt < d->st; ++rt)
+    for (int rh = 0; rh < d->sh; ++rh)
+      for (int rw = 0; rw < d->sw; ++rw) {
+        GatherProblem g;
+        int ntaps = 0;
+        if (dgrad_class(d, rt, rh, rw, &g, &ntaps) && ntaps == 0) any_empty = true;
+      }
+  if (any_empty) {
+    const size_t bytes = (size_t)d->B * d->Ti * d->Hi * d->Wi * d->Cp * 2;
+    cudaError_t e = addend != nullptr ? cudaMemcpyAsync(dx, addend, bytes, cudaMemcpyDeviceToDevice, s)
+                                      : cudaMemsetAsync(dx, 0, bytes, s);
+    DP_REQUIRE(e == cudaSuccess, DP_ERR_CUDA, "tcgen05 dgrad: clearing dx failed: %s", cudaGetErrorString(e));
+  }
+  for (int rt = 0; rt < d->st; ++rt)
+    for (int rh = 0; rh < d->sh; ++rh)
+      for (int rw = 0; rw < d->sw; ++rw) {
+        GatherProblem g;
+        int ntaps = 0;
+        if (!dgrad_class(d, rt, rh, rw, &g, &ntaps) || ntaps == 0) continue;
+        const int rc = launch_gather(g, dy, w, dx, addend, nullptr, nullptr, s);
+        if (rc != DP_OK) return rc;
+      }
+  return DP_OK;
 }
 
 }  // namespace dp
