@@ -81,6 +81,7 @@ class Conv3dBlock(nn.Module):
             raise NotImplementedError("dp_b200: Conv3dBlock(bias=True) is not on the R(2+1)D path (all its convs are bias-free)")
         self._cfg = Fn.LayerCfg(in_channels, out_channels, kernel_sizes, strides, paddings, alpha)
         self._packed = Fn.PackedWeights()
+        self._packed_stem = Fn.PackedWeights()
 
     def _refresh_cfg(self):
         c = self._cfg
@@ -89,6 +90,30 @@ class Conv3dBlock(nn.Module):
         if self.bn.momentum is None:
             raise NotImplementedError("dp_b200: BatchNorm3d(momentum=None) (cumulative average) is not supported")
         c.momentum = float(self.bn.momentum)
+
+    def _stem_geom(self, x: torch.Tensor):
+        """Geometry of the packed-rows stem fast path if it applies to this block and this caller-facing clip
+        (NCDHW fp32 without grad, or (B,T,H,W,3) uint8 frames), else None."""
+        if Fn.is_internal(x) or not x.is_cuda or x.dim() != 5 or x.requires_grad:
+            return None
+        if x.dtype == torch.uint8:
+            B, T, H, W, Cc = x.shape
+        elif x.dtype == torch.float32:
+            B, Cc, T, H, W = x.shape
+        else:
+            return None
+        if Cc != self._cfg.C:
+            return None
+        return Fn.stem_geom(self._cfg, B, T, H, W)
+
+    def forward_stem(self, x: torch.Tensor, geom, mean_bgr=None):
+        """External clip in, INTERNAL activation out (used by R2Plus1DNet for its first layer)."""
+        self._refresh_cfg()
+        xp = Fn.stem_pack_input(x, geom, mean_bgr)
+        z = Fn.StemConvBnActFn.apply(xp, self.conv.weight, self.bn.weight, self.bn.bias, self, geom)
+        if self.training and self.bn.track_running_stats:
+            self.bn.num_batches_tracked.add_(1)
+        return Fn.tag(z, self._cfg.K)
 
     def forward(self, x: torch.Tensor):
         x, was_internal = _enter(x)
@@ -222,10 +247,21 @@ class R2Plus1DNet(nn.Module):
         self.pool = nn.AdaptiveAvgPool3d(1)
         self.out_features = 128
 
-    def forward(self, x: torch.Tensor):
+    def forward(self, x: torch.Tensor, mean_bgr=None):
+        """x: (B,3,T,H,W) fp32 clips as the reference's DataLoader yields them, or -- an extension for the
+        sliding-window loop -- (B,T,H,W,3) uint8 BGR frames with `mean_bgr` (dataset.py:104-110)."""
         batch_size = x.size(0)
-        x, _ = _enter(x)
-        for stage in (self.conv1, self.conv2, self.conv3, self.conv4, self.conv5):
+        stem = self.conv1.spatio_conv
+        geom = None if (_hooked(self.conv1) or _hooked(stem) or _hooked(self.conv1.temporal_conv)) else stem._stem_geom(x)
+        if geom is not None:
+            x = _call(self.conv1.temporal_conv, stem.forward_stem(x, geom, mean_bgr))
+            stages = (self.conv2, self.conv3, self.conv4, self.conv5)
+        else:
+            if x.dtype == torch.uint8:
+                x = Fn.frames_u8_to_internal(x, mean_bgr)
+            x, _ = _enter(x)
+            stages = (self.conv1, self.conv2, self.conv3, self.conv4, self.conv5)
+        for stage in stages:
             x = _call(stage, x)
         x = Fn.AvgPoolFn.apply(x, x._dp_c)
         return x.view(batch_size, -1)

@@ -54,6 +54,14 @@ SIGNATURES = {
     "dp_conv_dgrad": (_i, [_pdesc, _vp, _vp, _vp, _vp, _i, _vp]),
     "dp_conv_wgrad_workspace": (_sz, [_pdesc, _i]),
     "dp_conv_wgrad": (_i, [_pdesc, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "dp_stem_supported": (_i, [_pdesc]),
+    "dp_stem_input_elems": (_sz, [_pdesc]),
+    "dp_stem_pack_input_f32": (_i, [_pdesc, _vp, _vp, _vp]),
+    "dp_stem_pack_input_u8": (_i, [_pdesc, _vp, C.POINTER(C.c_float), _vp, _vp]),
+    "dp_stem_pack_weights": (_i, [_pdesc, _vp, _vp, _vp]),
+    "dp_stem_conv_fwd": (_i, [_pdesc, _vp, _vp, _vp, _vp, _pint, _vp]),
+    "dp_stem_wgrad_workspace": (_sz, [_pdesc]),
+    "dp_stem_conv_wgrad": (_i, [_pdesc, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dp_bn_stats": (_i, [_vp, _i64, _i, _i, _vp, _pint, _vp]),
     "dp_bn_finalize": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dp_bn_eval_coeffs": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp]),

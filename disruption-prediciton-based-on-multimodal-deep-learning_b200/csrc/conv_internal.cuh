@@ -30,6 +30,12 @@ size_t tc_wgrad_workspace(const dp_conv_desc* d);
 int tc_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t s);
 
+// same kernels over a strided / overlapping VIEW of x (element strides of w,h,t,b): the packed stem rows
+int tc_conv_fwd_view(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* w, void* y,
+                     float* part, int* nparts, cudaStream_t s);
+int tc_conv_wgrad_view(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* dy, float* dw,
+                       void* ws, size_t ws_bytes, cudaStream_t s);
+
 // BN partial statistics over a finished tensor (bn_act.cu)
 int bn_stats_launch(const void* y, int64_t rows, int Cp, int dtype, float* part, int* nparts, cudaStream_t s);
 

@@ -305,6 +305,8 @@ struct GatherProblem {
   // destination view inside the full tensor (FT,FH,FW): origin and step per dim (strided dgrad parity classes)
   int FT, FH, FW;
   int vo_t, vo_h, vo_w, vs_t, vs_h, vs_w;
+  // optional source view: element strides of (w,h,t,b); 0 = dense NDHWC (the packed stem rows overlap in w)
+  long long ss_w, ss_h, ss_t, ss_b;
 };
 
 struct TcPlan {
@@ -447,12 +449,14 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
 }
 
 static int encode_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, const int* box,
-                          const int* estride, CUtensorMapSwizzle sw) {
+                          const int* estride, CUtensorMapSwizzle sw, const long long* vstr = nullptr) {
   PFN_encodeTiled enc = get_encode();
   DP_REQUIRE(enc != nullptr, DP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
                            (cuuint64_t)T * H * W * C * 2};
+  if (vstr != nullptr && vstr[0] > 0)
+    for (int i = 0; i < 4; ++i) strides[i] = (cuuint64_t)vstr[i] * 2;
   cuuint32_t b[5], es[5];
   for (int i = 0; i < 5; ++i) { b[i] = (cuuint32_t)box[i]; es[i] = (cuuint32_t)estride[i]; }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, b, es,
@@ -505,7 +509,8 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   const CUtensorMapSwizzle sw = p.CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                            : (p.CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap tmA, tmB, tmD;
-  int rc = encode_act_map(&tmA, src, g.sC, g.sW, g.sH, g.sT, g.B, plan.a_box, plan.a_estride, sw);
+  const long long vstr[4] = {g.ss_w, g.ss_h, g.ss_t, g.ss_b};
+  int rc = encode_act_map(&tmA, src, g.sC, g.sW, g.sH, g.sT, g.B, plan.a_box, plan.a_estride, sw, vstr);
   if (rc != DP_OK) return rc;
   const int taps = g.Kt * g.Kh * g.Kw;
   rc = encode_wgt_map(&tmB, wgt, taps * g.sC, g.dC, p.CB, p.Ntile, sw);
@@ -546,6 +551,7 @@ static GatherProblem fwd_problem(const dp_conv_desc* d) {
   g.FT = g.dT; g.FH = g.dH; g.FW = g.dW;
   g.vo_t = g.vo_h = g.vo_w = 0;
   g.vs_t = g.vs_h = g.vs_w = 1;
+  g.ss_w = g.ss_h = g.ss_t = g.ss_b = 0;
   return g;
 }
 
@@ -579,6 +585,7 @@ static bool dgrad_class(const dp_conv_desc* d, int rt, int rh, int rw, GatherPro
   g->FT = d->Ti; g->FH = d->Hi; g->FW = d->Wi;
   g->vo_t = rt; g->vo_h = rh; g->vo_w = rw;
   g->vs_t = st[0]; g->vs_h = st[1]; g->vs_w = st[2];
+  g->ss_w = g->ss_h = g->ss_t = g->ss_b = 0;
   *ntaps = cnt[0] * cnt[1] * cnt[2];
   return true;
 }
@@ -609,6 +616,15 @@ bool tc_dgrad_supported(const dp_conv_desc* d) {
 int tc_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, float* part, int* nparts,
                 cudaStream_t s) {
   return launch_gather(fwd_problem(d), x, w, y, nullptr, part, nparts, s);
+}
+
+bool tc_fwd_view_supported(const dp_conv_desc* d) { return tc_fwd_supported(d); }
+
+int tc_conv_fwd_view(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* w, void* y,
+                     float* part, int* nparts, cudaStream_t s) {
+  GatherProblem g = fwd_problem(d);
+  g.ss_w = xstrides[0]; g.ss_h = xstrides[1]; g.ss_t = xstrides[2]; g.ss_b = xstrides[3];
+  return launch_gather(g, x, w, y, nullptr, part, nparts, s);
 }
 
 int tc_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,

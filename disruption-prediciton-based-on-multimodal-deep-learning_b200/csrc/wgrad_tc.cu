@@ -430,12 +430,14 @@ static bool plan_wgrad(const dp_conv_desc* d, WgPlan* out) {
 }
 
 static int wg_encode_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, const int* box,
-                         const int* estride, int cb) {
+                         const int* estride, int cb, const long long* vstr = nullptr) {
   PFN_encodeTiled enc = wg_get_encode();
   DP_REQUIRE(enc != nullptr, DP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
                            (cuuint64_t)T * H * W * C * 2};
+  if (vstr != nullptr && vstr[0] > 0)
+    for (int i = 0; i < 4; ++i) strides[i] = (cuuint64_t)vstr[i] * 2;
   cuuint32_t b[5], es[5];
   for (int i = 0; i < 5; ++i) { b[i] = (cuuint32_t)box[i]; es[i] = (cuuint32_t)estride[i]; }
   const CUtensorMapSwizzle sw = cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -462,6 +464,11 @@ size_t tc_wgrad_workspace(const dp_conv_desc* d) {
 
 int tc_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t s) {
+  return tc_conv_wgrad_view(d, nullptr, x, dy, dw, ws, ws_bytes, s);
+}
+
+int tc_conv_wgrad_view(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* dy, float* dw,
+                       void* ws, size_t ws_bytes, cudaStream_t s) {
   WgPlan plan;
   DP_REQUIRE(plan_wgrad(d, &plan), DP_ERR_UNSUPPORTED, "tcgen05 wgrad: geometry not supported");
   DP_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)ws & 15) == 0, DP_ERR_ALIGN,
@@ -470,7 +477,7 @@ int tc_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* d
   DP_REQUIRE(ws_bytes >= (size_t)p.nsplit * d->Kp * p.taps * d->Cp * sizeof(float), DP_ERR_SHAPE,
              "tcgen05 wgrad: workspace too small");
   CUtensorMap tmX, tmD;
-  int rc = wg_encode_map(&tmX, x, d->Cp, d->Wi, d->Hi, d->Ti, d->B, plan.x_box, plan.x_estride, p.cbX);
+  int rc = wg_encode_map(&tmX, x, d->Cp, d->Wi, d->Hi, d->Ti, d->B, plan.x_box, plan.x_estride, p.cbX, xstrides);
   if (rc != DP_OK) return rc;
   const int ones[5] = {1, 1, 1, 1, 1};
   rc = wg_encode_map(&tmD, dy, d->Kp, d->Wo, d->Ho, d->To, d->B, plan.d_box, ones, p.cbD);

@@ -117,7 +117,7 @@ def _p(t: Optional[torch.Tensor]):
 # ----------------------------------------------------------------------------------------------
 class ConvGeom:
     __slots__ = ("desc", "rows_out", "rows_in", "out_shape", "in_shape", "taps", "ws_bytes", "key", "flops", "esize",
-                 "fam")
+                 "fam", "stem")
 
     def __init__(self, C_in, K, kernel, stride, padding, B, T, H, W, dtype_code):
         kt, kh, kw = kernel
@@ -139,9 +139,12 @@ class ConvGeom:
         self.flops = 2.0 * self.rows_out * K * C_in * self.taps      # algorithmic (unpadded) FLOPs of one pass
         self.esize = 2 if dtype_code == L.DP_BF16 else 4
         self.fam = None
+        self.stem = False   # True: x is the packed-rows clip of the stem fast path (csrc/stem.cu)
 
     def families(self, impl):
         """Which kernel family serves fwd / dgrad / wgrad for this geometry (profiling labels)."""
+        if self.stem:
+            return (impl, "tc_gather_gemm", "tc_gather_gemm", "tc_wgrad")
         if self.fam is None or self.fam[0] != impl:
             lib = L.load()
             tc = [bool(impl != L.IMPL_SIMT and lib.dp_conv_supported(C.byref(self.desc), op, L.IMPL_TC)) for op in range(3)]
@@ -305,33 +308,48 @@ def pack_weights(weight: torch.Tensor, geom: ConvGeom, dtype: torch.dtype, cache
     d = geom.desc
     if weight.dtype != torch.float32 or not weight.is_contiguous():
         raise L.DpError("conv master weights must be contiguous float32")
-    wf = torch.empty((d.Kp, geom.taps, d.Cp), dtype=dtype, device=weight.device)
-    wd = torch.empty((d.Cp, geom.taps, d.Kp), dtype=dtype, device=weight.device)
-    L.check(L.load().dp_pack_weights(C.byref(d), weight.data_ptr(), wf.data_ptr(), wd.data_ptr(), L.stream_ptr()),
-            "dp_pack_weights")
+    if geom.stem:
+        wf = torch.empty((d.Kp, d.kh, 32), dtype=torch.bfloat16, device=weight.device)
+        wd = wf   # no data gradient on the stem path
+        L.check(L.load().dp_stem_pack_weights(C.byref(d), weight.data_ptr(), wf.data_ptr(), L.stream_ptr()),
+                "dp_stem_pack_weights")
+    else:
+        wf = torch.empty((d.Kp, geom.taps, d.Cp), dtype=dtype, device=weight.device)
+        wd = torch.empty((d.Cp, geom.taps, d.Kp), dtype=dtype, device=weight.device)
+        L.check(L.load().dp_pack_weights(C.byref(d), weight.data_ptr(), wf.data_ptr(), wd.data_ptr(), L.stream_ptr()),
+                "dp_pack_weights")
     if cache is not None:
         cache.version, cache.ptr, cache.dtype, cache.wf, cache.wd = version, weight.data_ptr(), dtype, wf, wd
     return wf, wd
 
 
+def _conv_fwd_call(lib, geom, x, wf, y, part, nparts, impl, st):
+    d = geom.desc
+    if geom.stem:
+        return lib.dp_stem_conv_fwd(C.byref(d), x.data_ptr(), wf.data_ptr(), y.data_ptr(), part, nparts, st)
+    return lib.dp_conv_fwd(C.byref(d), x.data_ptr(), wf.data_ptr(), y.data_ptr(), part, nparts, impl, st)
+
+
 def layer_forward(x, weight, gamma, beta, running_mean, running_var, cfg: LayerCfg, training: bool,
-                  residual=None, slope_res: float = 1.0, cache: Optional[PackedWeights] = None):
-    """Returns (z, saved) with saved = (x, y, out_or_None, stats[4,Kp], w_dgrad, geom)."""
+                  residual=None, slope_res: float = 1.0, cache: Optional[PackedWeights] = None, geom=None):
+    """Returns (z, saved) with saved = (x, y, out_or_None, stats[4,Kp], w_dgrad, geom).
+    `geom` is given only by the stem fast path, where x is the packed-rows clip."""
     lib = L.load()
     st = L.stream_ptr()
-    geom = conv_geom(cfg.C, cfg.K, cfg.kernel, cfg.stride, cfg.padding, x)
+    if geom is None:
+        geom = conv_geom(cfg.C, cfg.K, cfg.kernel, cfg.stride, cfg.padding, x)
     d = geom.desc
-    wf, wd = pack_weights(weight, geom, x.dtype, cache)
+    act_dtype = torch.bfloat16 if geom.stem else x.dtype
+    wf, wd = pack_weights(weight, geom, act_dtype, cache)
     dev = x.device
-    y = torch.empty(geom.out_shape, dtype=x.dtype, device=dev)
+    y = torch.empty(geom.out_shape, dtype=act_dtype, device=dev)
     stats = torch.empty((4, d.Kp), dtype=torch.float32, device=dev)  # mean, rstd, scale, shift
     impl = _STATE["impl"]
     if training:
         part = torch.empty((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=dev)
         nparts = C.c_int(0)
         t0 = _pb()
-        L.check(lib.dp_conv_fwd(C.byref(d), x.data_ptr(), wf.data_ptr(), y.data_ptr(), part.data_ptr(),
-                                C.byref(nparts), impl, st), "dp_conv_fwd")
+        L.check(_conv_fwd_call(lib, geom, x, wf, y, part.data_ptr(), C.byref(nparts), impl, st), "dp_conv_fwd")
         if t0 is not None:
             _pe(t0, geom.families(impl)[1], geom.flops, geom.esize * (geom.rows_in * d.C + geom.rows_out * d.K))
         L.check(lib.dp_bn_finalize(part.data_ptr(), nparts.value, d.K, d.Kp, float(geom.rows_out), gamma.data_ptr(),
@@ -339,8 +357,7 @@ def layer_forward(x, weight, gamma, beta, running_mean, running_var, cfg: LayerC
                                    stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
                                    st), "dp_bn_finalize")
     else:
-        L.check(lib.dp_conv_fwd(C.byref(d), x.data_ptr(), wf.data_ptr(), y.data_ptr(), None, None, impl, st),
-                "dp_conv_fwd")
+        L.check(_conv_fwd_call(lib, geom, x, wf, y, None, None, impl, st), "dp_conv_fwd")
         if running_mean is None or running_var is None:
             raise L.DpError("eval-mode BatchNorm needs running statistics")
         stats.zero_()
@@ -399,12 +416,19 @@ def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope
     impl = _STATE["impl"]
     dw = torch.empty(weight_shape, dtype=torch.float32, device=dev)
     if geom.ws_bytes is None:
-        geom.ws_bytes = int(lib.dp_conv_wgrad_workspace(C.byref(d), impl))
+        geom.ws_bytes = int(lib.dp_stem_wgrad_workspace(C.byref(d)) if geom.stem
+                            else lib.dp_conv_wgrad_workspace(C.byref(d), impl))
     ws = _workspace(geom.ws_bytes, dev)
     io_bytes = geom.esize * (geom.rows_in * d.C + geom.rows_out * d.K)
     t0 = _pb()
-    L.check(lib.dp_conv_wgrad(C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(), impl,
-                              st), "dp_conv_wgrad")
+    if geom.stem:
+        if need_dx:
+            raise L.DpError("the stem fast path has no data gradient")
+        L.check(lib.dp_stem_conv_wgrad(C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       st), "dp_stem_conv_wgrad")
+    else:
+        L.check(lib.dp_conv_wgrad(C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  impl, st), "dp_conv_wgrad")
     if t0 is not None:
         _pe(t0, geom.families(impl)[3], geom.flops, io_bytes)
     dx = None
@@ -449,6 +473,67 @@ class ConvBnActFn(torch.autograd.Function):
         dx, dw, dg, db, _ = layer_backward((xs, y, None, stats, wd, ctx.geom), dz, ctx.wshape, ctx.cfg, ctx.training,
                                            1.0, ctx.needs_input_grad[0])
         return dx, dw, dg, db, None
+
+
+_STEM_GEOMS = {}
+
+
+def stem_geom(cfg: LayerCfg, B: int, T: int, H: int, W: int) -> Optional[ConvGeom]:
+    """Geometry of the stem fast path for this Conv3dBlock and clip size, or None if it does not apply
+    (fp32 validation mode, other kernels/strides, or the tcgen05 kernels disabled)."""
+    if _STATE["dtype"] != torch.bfloat16 or _STATE["impl"] == L.IMPL_SIMT:
+        return None
+    key = (cfg.C, cfg.K, cfg.kernel, cfg.stride, cfg.padding, B, T, H, W)
+    g = _STEM_GEOMS.get(key)
+    if g is None:
+        g = ConvGeom(cfg.C, cfg.K, cfg.kernel, cfg.stride, cfg.padding, B, T, H, W, L.DP_BF16)
+        g.stem = True
+        if not L.load().dp_stem_supported(C.byref(g.desc)):
+            g = False
+        _STEM_GEOMS[key] = g
+    return g or None
+
+
+def stem_pack_input(x: torch.Tensor, geom: ConvGeom, mean_bgr=None) -> torch.Tensor:
+    """NCDHW fp32 clip (or (B,T,H,W,3) uint8 frames + BGR mean) -> packed rows XP for the stem fast path."""
+    L.require_device()
+    lib = L.load()
+    d = geom.desc
+    xp = torch.empty(int(lib.dp_stem_input_elems(C.byref(d))), dtype=torch.bfloat16, device=x.device)
+    x = x.contiguous()
+    if x.dtype == torch.uint8:
+        m = (C.c_float * 3)(*[float(v) for v in mean_bgr])
+        L.check(lib.dp_stem_pack_input_u8(C.byref(d), x.data_ptr(), m, xp.data_ptr(), L.stream_ptr()),
+                "dp_stem_pack_input_u8")
+    else:
+        L.check(lib.dp_stem_pack_input_f32(C.byref(d), x.data_ptr(), xp.data_ptr(), L.stream_ptr()),
+                "dp_stem_pack_input_f32")
+    return xp
+
+
+class StemConvBnActFn(torch.autograd.Function):
+    """The stem Conv3dBlock on the packed-rows fast path.  inputs: xp (packed clip, no grad), weight, gamma,
+    beta, mod, geom."""
+
+    @staticmethod
+    def forward(ctx, xp, weight, gamma, beta, mod, geom):
+        training = mod.training
+        rm, rv = (mod.bn.running_mean, mod.bn.running_var) if mod.bn.track_running_stats else (None, None)
+        if not training and rm is None:
+            training = True
+        z, saved = layer_forward(xp, weight, gamma, beta, rm, rv, mod._cfg, training, cache=mod._packed_stem, geom=geom)
+        _, y, _, stats, _, _ = saved
+        ctx.save_for_backward(xp, y, stats)
+        ctx.geom, ctx.cfg, ctx.training, ctx.wshape = geom, mod._cfg, training, weight.shape
+        return z
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dz):
+        xp, y, stats = ctx.saved_tensors
+        _, dw, dg, db, _ = layer_backward((xp, y, None, stats, None, ctx.geom), dz, ctx.wshape, ctx.cfg, ctx.training,
+                                          1.0, False)
+        return None, dw, dg, db, None, None
 
 
 class AddActFn(torch.autograd.Function):

@@ -40,8 +40,7 @@ def sliding_window_probs(model: torch.nn.Module, frames_u8: torch.Tensor, seq_le
             e = min(rng.stop, s + batch_size)
             starts = torch.arange(s, e, device=frames_u8.device)
             clip = frames_u8[(starts[:, None] + idx0[None, :])]          # (b, T, H, W, 3) uint8 gather
-            x = Fn.frames_u8_to_internal(clip, mean_bgr)                 # fused mean-subtract + layout
-            feat = enc(x)
+            feat = enc(clip, mean_bgr)                                   # fused mean-subtract + layout in the stem
             logits = model.linear(feat)
             probs.append(torch.softmax(logits, dim=1)[:, 0])
     finally:

@@ -103,6 +103,22 @@ size_t dp_conv_wgrad_workspace(const dp_conv_desc* d, int impl);
 int dp_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw,
                   void* workspace, size_t workspace_bytes, int impl, void* stream);
 
+/* ---- stem fast path: C <= 4 input channels, kernel (1,kh,kw<=8), stride (1,sh,2), bf16 (R2Plus1D.py:137-140) ----
+ * The clip is kept as packed rows XP[b][t][h][wp][4] (wp = w + pw, WP = 2*Wo + 6, zero padded) instead of
+ * 16-channel NDHWC; forward and weight gradient run on the tcgen05 kernels over an overlapping-window view.
+ * There is no data gradient on this path (clips carry no gradient). */
+int    dp_stem_supported(const dp_conv_desc* d);
+size_t dp_stem_input_elems(const dp_conv_desc* d);            /* bf16 elements of XP */
+int    dp_stem_pack_input_f32(const dp_conv_desc* d, const float* ncdhw, void* xp, void* stream);
+int    dp_stem_pack_input_u8(const dp_conv_desc* d, const uint8_t* frames /* (B,T,H,W,3) */, const float* mean3,
+                             void* xp, void* stream);
+int    dp_stem_pack_weights(const dp_conv_desc* d, const float* w, void* wv /* [Kp][kh][32] bf16 */, void* stream);
+int    dp_stem_conv_fwd(const dp_conv_desc* d, const void* xp, const void* wv, void* y, float* part, int* nparts,
+                        void* stream);
+size_t dp_stem_wgrad_workspace(const dp_conv_desc* d);
+int    dp_stem_conv_wgrad(const dp_conv_desc* d, const void* xp, const void* dy, float* dw, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* ---- BatchNorm3d (train) + LeakyReLU (R2Plus1D.py:53-57,179-187) ---- */
 int dp_bn_stats(const void* y, int64_t rows, int Cp, int dtype, float* part, int* nparts, void* stream);
 int dp_bn_finalize(const float* part, int nparts, int C, int Cp, double count,

@@ -236,6 +236,51 @@ def test_conv_tcgen05_modes():
         L.set_option("wg_halo", 1)
 
 
+@pytest.mark.parametrize("shape", [(2, 5, 32, 32), (2, 21, 128, 128), (1, 3, 50, 38)])
+@pytest.mark.parametrize("u8", [False, True])
+def test_stem_fast_path(shape, u8):
+    """Packed-rows stem (csrc/stem.cu): forward + BN partials + weight gradient against fp64 conv3d on the same
+    bf16-rounded operands, from NCDHW fp32 clips and from uint8 frames."""
+    B, T, H, W = shape
+    lib = L.load()
+    k, s_, p_ = (1, 7, 7), (1, 2, 2), (0, 3, 3)
+    g = torch.Generator().manual_seed(4)
+    frames = torch.randint(0, 256, (B, T, H, W, 3), generator=g, dtype=torch.uint8)
+    mean = (90.0, 98.0, 102.0)
+    x = (frames.float() - torch.tensor(mean)).permute(0, 4, 1, 2, 3).contiguous()     # NCDHW, exactly bf16-representable
+    w = (torch.randn(45, 3, *k, generator=g) * math.sqrt(2.0 / 147)).bfloat16().float()
+    x, w, frames = x.to(DEV), w.to(DEV), frames.to(DEV)
+    cfg = Fn.LayerCfg(3, 45, k, s_, p_, 1.0)
+    with dp_b200.compute_mode("bf16", "auto"):
+        gm = Fn.stem_geom(cfg, B, T, H, W)
+    assert gm is not None, "stem fast path must cover the R(2+1)D stem geometry"
+    d = gm.desc
+    xp = Fn.stem_pack_input(frames if u8 else x, gm, mean)
+    wv, _ = Fn.pack_weights(w, gm, torch.bfloat16, None)
+    y = torch.full(gm.out_shape, float("nan"), dtype=torch.bfloat16, device=DEV)
+    part = torch.zeros((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=DEV)
+    nparts = C.c_int(0)
+    L.check(lib.dp_stem_conv_fwd(C.byref(d), xp.data_ptr(), wv.data_ptr(), y.data_ptr(), part.data_ptr(),
+                                 C.byref(nparts), L.stream_ptr()), "stem fwd")
+    geom = (3, 45, k, s_, p_, T, H, W)
+    ref = torch_ref(geom, x, w)
+    yo = from_int(y, 45)
+    assert torch.isfinite(y.float()).all()
+    assert rel_err(yo, ref["y"]) < 2 ** -7
+    assert (y[..., 45:] == 0).all()
+    st = part[:nparts.value].double().sum(0)
+    assert rel_err(st[0, :45], yo.double().sum(dim=(0, 2, 3, 4))) < 1e-3
+    assert rel_err(st[1, :45], (yo.double() ** 2).sum(dim=(0, 2, 3, 4))) < 1e-3
+    dy = torch.randn_like(ref["y"], dtype=torch.float32).bfloat16().float()
+    ref = torch_ref(geom, x, w, dy)
+    dyi = to_int(dy, torch.bfloat16)
+    dw = torch.full_like(w, float("nan"))
+    ws = torch.empty(int(lib.dp_stem_wgrad_workspace(C.byref(d))), dtype=torch.uint8, device=DEV)
+    L.check(lib.dp_stem_conv_wgrad(C.byref(d), xp.data_ptr(), dyi.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   L.stream_ptr()), "stem wgrad")
+    assert rel_err(dw, ref["dw"]) < 1e-3
+
+
 # ---- BatchNorm / activation ------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("C_", [32, 45, 72, 288])
