@@ -16,7 +16,7 @@ constexpr int RED_THREADS = 256;
 // F: __device__ void operator()(int64_t elem_offset, int c0, float* a8, float* b8) accumulates 8 channels
 template <typename F>
 __global__ void __launch_bounds__(RED_THREADS)
-col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part) {
+col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part) {  // f by value: per-thread register copy
   __shared__ float red[2][RED_THREADS * 8];
   const int vpr = Cp >> 3;                       // 8-channel vectors per row
   const int rpi = RED_THREADS / vpr;             // rows per iteration
@@ -31,7 +31,13 @@ col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part) {
   for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; }
   if (tid < active) {
     const int cv = tid % vpr, rl = tid / vpr;
-    for (int64_t r = r0 + rl; r < r1; r += rpi) f(r * Cp + cv * 8, cv * 8, a, b);
+    f.init(cv * 8);                       // this thread's 8 channels never change: parameters live in registers
+    int64_t r = r0 + rl;
+    for (; r + rpi < r1; r += 2 * rpi) {  // two independent rows in flight
+      f(r * Cp + cv * 8, a, b);
+      f((r + rpi) * Cp + cv * 8, a, b);
+    }
+    if (r < r1) f(r * Cp + cv * 8, a, b);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[0][tid * 8 + j] = a[j]; red[1][tid * 8 + j] = b[j]; }
@@ -55,7 +61,8 @@ static int reduce_grid(int64_t rows) {
 template <typename T>
 struct StatsF {
   const T* y;
-  __device__ __forceinline__ void operator()(int64_t off, int, float* a, float* b) const {
+  __device__ __forceinline__ void init(int) {}
+  __device__ __forceinline__ void operator()(int64_t off, float* a, float* b) const {
     const f8 v = ld8(y + off);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a[j] += v.v[j]; b[j] = fmaf(v.v[j], v.v[j], b[j]); }
@@ -67,18 +74,24 @@ struct BwdReduceF {
   const T* dz; const T* y; const T* out;
   const float* scale; const float* shift; const float* mean; const float* rstd;
   float slope, slope_res;
-  __device__ __forceinline__ void operator()(int64_t off, int c0, float* a, float* b) const {
+  float r_scale[8], r_shift[8], r_mean[8], r_rstd[8];
+  __device__ __forceinline__ void init(int c0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      r_scale[j] = scale[c0 + j]; r_shift[j] = shift[c0 + j]; r_mean[j] = mean[c0 + j]; r_rstd[j] = rstd[c0 + j];
+    }
+  }
+  __device__ __forceinline__ void operator()(int64_t off, float* a, float* b) const {
     const f8 g = ld8(dz + off), v = ld8(y + off);
     f8 o;
     if (out != nullptr) o = ld8(out + off);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
       float gg = g.v[j];
       if (out != nullptr) gg *= (o.v[j] > 0.f ? 1.f : slope_res);
-      const float u = fmaf(v.v[j], __ldg(scale + c), __ldg(shift + c));
+      const float u = fmaf(v.v[j], r_scale[j], r_shift[j]);
       gg *= (u > 0.f ? 1.f : slope);
-      const float xh = (v.v[j] - __ldg(mean + c)) * __ldg(rstd + c);
+      const float xh = (v.v[j] - r_mean[j]) * r_rstd[j];
       a[j] += gg;
       b[j] = fmaf(gg, xh, b[j]);
     }
@@ -101,18 +114,40 @@ int bn_stats_launch(const void* y, int64_t rows, int Cp, int dtype, float* part,
 }
 
 // ---- finalize: partials -> mean/rstd/scale/shift, running stats (momentum, unbiased var) ----
-__global__ void bn_finalize_kernel(const float* __restrict__ part, int nparts, int C, int Cp, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float momentum, float* running_mean, float* running_var,
-                                   float* mean, float* rstd, float* scale, float* shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Cp) return;
-  if (c >= C) { mean[c] = 0.f; rstd[c] = 0.f; scale[c] = 0.f; shift[c] = 0.f; return; }
-  double S = 0.0, Q = 0.0;
-  for (int p = 0; p < nparts; ++p) {
-    S += (double)part[((int64_t)p * 2 + 0) * Cp + c];
-    Q += (double)part[((int64_t)p * 2 + 1) * Cp + c];
+// One CTA of 256 threads per 32 channels: 8 part-lanes x 32 channel-lanes, fp64 partial sums combined in a fixed
+// order (deterministic), reads coalesced along the channel dimension.
+constexpr int FIN_CH = 32, FIN_PL = 8;
+__device__ __forceinline__ void fin_reduce(const float* __restrict__ part, int nparts, int Cp, int c, int pl, bool cval,
+                                           double& S, double& Q, double (*red)[FIN_PL][FIN_CH]) {
+  double s = 0.0, q = 0.0;
+  if (cval) {
+    for (int p = pl; p < nparts; p += FIN_PL) {
+      s += (double)part[((int64_t)p * 2 + 0) * Cp + c];
+      q += (double)part[((int64_t)p * 2 + 1) * Cp + c];
+    }
   }
+  const int cl = threadIdx.x % FIN_CH;
+  red[0][pl][cl] = s;
+  red[1][pl][cl] = q;
+  __syncthreads();
+  S = 0.0; Q = 0.0;
+  if (pl == 0) {
+#pragma unroll
+    for (int i = 0; i < FIN_PL; ++i) { S += red[0][i][cl]; Q += red[1][i][cl]; }
+  }
+}
+
+__global__ void __launch_bounds__(FIN_CH * FIN_PL)
+bn_finalize_kernel(const float* __restrict__ part, int nparts, int C, int Cp, double count,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   float momentum, float* running_mean, float* running_var,
+                   float* mean, float* rstd, float* scale, float* shift) {
+  __shared__ double red[2][FIN_PL][FIN_CH];
+  const int c = blockIdx.x * FIN_CH + threadIdx.x % FIN_CH, pl = threadIdx.x / FIN_CH;
+  double S, Q;
+  fin_reduce(part, nparts, Cp, c, pl, c < C, S, Q, red);
+  if (pl != 0 || c >= Cp) return;
+  if (c >= C) { mean[c] = 0.f; rstd[c] = 0.f; scale[c] = 0.f; shift[c] = 0.f; return; }
   const double mu = S / count;
   double var = Q / count - mu * mu;
   if (var < 0.0) var = 0.0;
@@ -140,16 +175,15 @@ __global__ void bn_eval_coeffs_kernel(const float* rm, const float* rv, const fl
   shift[c] = beta[c] - rm[c] * sc;
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, int Cp, double count,
-                                       float* dgamma, float* dbeta, float* coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Cp) return;
+__global__ void __launch_bounds__(FIN_CH * FIN_PL)
+bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, int Cp, double count,
+                       float* dgamma, float* dbeta, float* coef) {
+  __shared__ double red[2][FIN_PL][FIN_CH];
+  const int c = blockIdx.x * FIN_CH + threadIdx.x % FIN_CH, pl = threadIdx.x / FIN_CH;
+  double S, Q;
+  fin_reduce(part, nparts, Cp, c, pl, c < C, S, Q, red);
+  if (pl != 0 || c >= Cp) return;
   if (c >= C) { coef[c] = 0.f; coef[Cp + c] = 0.f; return; }
-  double S = 0.0, Q = 0.0;
-  for (int p = 0; p < nparts; ++p) {
-    S += (double)part[((int64_t)p * 2 + 0) * Cp + c];
-    Q += (double)part[((int64_t)p * 2 + 1) * Cp + c];
-  }
   if (dbeta != nullptr) dbeta[c] = (float)S;
   if (dgamma != nullptr) dgamma[c] = (float)Q;
   coef[c] = (float)(S / count);
@@ -157,26 +191,29 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int npart
 }
 
 // ---- elementwise passes ----
+// Grid-stride loops whose stride is a multiple of the vectors-per-row, so a thread always works on the same
+// 8 channels and keeps their parameters in registers (no per-element parameter traffic).
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_act_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                     float slope, const T* __restrict__ residual, float slope_res, T* __restrict__ z,
                     int64_t nvec, int Cp) {
-  extern __shared__ float sm[];
-  float* s_scale = sm;
-  float* s_shift = sm + Cp;
-  for (int c = threadIdx.x; c < Cp; c += blockDim.x) { s_scale[c] = scale[c]; s_shift[c] = shift[c]; }
-  __syncthreads();
   const int vpr = Cp >> 3;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    const int c0 = (int)(v % vpr) * 8;
+  const int64_t total = (int64_t)gridDim.x * blockDim.x;
+  const int64_t stride = (total / vpr) * vpr;
+  const int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v0 >= stride) return;
+  const int c0 = (int)(v0 % vpr) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+  for (int64_t v = v0; v < nvec; v += stride) {
     f8 a = ld8(y + v * 8);
     f8 r;
     if (residual != nullptr) r = ld8(residual + v * 8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float u = lrelu(fmaf(a.v[j], s_scale[c0 + j], s_shift[c0 + j]), slope);
+      float u = lrelu(fmaf(a.v[j], sc[j], sh[j]), slope);
       if (residual != nullptr) u = lrelu(u + r.v[j], slope_res);
       a.v[j] = u;
     }
@@ -191,35 +228,34 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y, const
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ coef, float slope, float slope_res,
                         T* __restrict__ dy, T* __restrict__ dres, int64_t nvec, int Cp) {
-  extern __shared__ float sm[];
-  float* s_scale = sm;
-  float* s_shift = sm + Cp;
-  float* s_mean = sm + 2 * Cp;
-  float* s_rstd = sm + 3 * Cp;
-  float* s_c0 = sm + 4 * Cp;
-  float* s_c1 = sm + 5 * Cp;
-  for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
-    s_scale[c] = scale[c]; s_shift[c] = shift[c]; s_mean[c] = mean[c]; s_rstd[c] = rstd[c];
-    s_c0[c] = coef[c]; s_c1[c] = coef[Cp + c];
-  }
-  __syncthreads();
   const int vpr = Cp >> 3;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    const int c0 = (int)(v % vpr) * 8;
+  const int64_t total = (int64_t)gridDim.x * blockDim.x;
+  const int64_t stride = (total / vpr) * vpr;
+  const int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v0 >= stride) return;
+  const int c0 = (int)(v0 % vpr) * 8;
+  // dy = scale*(g - c0 - xhat*c1),  xhat = (y - mean)*rstd   =>   dy = scale*g + ka + kb*y
+  float sc[8], sh[8], ka[8], kb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    sc[j] = scale[c]; sh[j] = shift[c];
+    const float c1r = coef[Cp + c] * rstd[c];
+    kb[j] = -sc[j] * c1r;
+    ka[j] = -sc[j] * (coef[c] - mean[c] * c1r);
+  }
+  for (int64_t v = v0; v < nvec; v += stride) {
     const f8 g = ld8(dz + v * 8), yy = ld8(y + v * 8);
     f8 o, res, d;
     if (out != nullptr) o = ld8(out + v * 8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
       float gg = g.v[j];
       if (out != nullptr) gg *= (o.v[j] > 0.f ? 1.f : slope_res);
       res.v[j] = gg;
-      const float u = fmaf(yy.v[j], s_scale[c], s_shift[c]);
+      const float u = fmaf(yy.v[j], sc[j], sh[j]);
       gg *= (u > 0.f ? 1.f : slope);
-      const float xh = (yy.v[j] - s_mean[c]) * s_rstd[c];
-      d.v[j] = s_scale[c] * (gg - s_c0[c] - xh * s_c1[c]);
+      d.v[j] = fmaf(sc[j], gg, fmaf(kb[j], yy.v[j], ka[j]));
     }
     st8(dy + v * 8, d);
     if (dres != nullptr) st8(dres + v * 8, res);
@@ -239,10 +275,12 @@ add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, 
   }
 }
 
-static int ew_grid(int64_t nvec) {
+static int ew_grid(int64_t nvec, int vpr) {
   int64_t g = (nvec + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 8;
   if (g > cap) g = cap;
+  const int64_t gmin = (vpr + 255) / 256;   // the loop stride must hold at least one full row of vectors
+  if (g < gmin) g = gmin;
   if (g < 1) g = 1;
   return (int)g;
 }
@@ -264,7 +302,7 @@ DP_API int dp_bn_finalize(const float* part, int nparts, int C, int Cp, double c
              "dp_bn_finalize: bad sizes (nparts=%d C=%d Cp=%d)", nparts, C, Cp);
   DP_REQUIRE((running_mean == nullptr) == (running_var == nullptr), DP_ERR_SHAPE,
              "dp_bn_finalize: running_mean/var must both be given or both NULL");
-  bn_finalize_kernel<<<ceil_div(Cp, 128), 128, 0, as_stream(stream)>>>(part, nparts, C, Cp, count, gamma, beta, eps,
+  bn_finalize_kernel<<<ceil_div(Cp, FIN_CH), FIN_CH * FIN_PL, 0, as_stream(stream)>>>(part, nparts, C, Cp, count, gamma, beta, eps,
                                                                       momentum, running_mean, running_var, mean, rstd,
                                                                       scale, shift);
   return check_launch("dp_bn_finalize");
@@ -284,8 +322,8 @@ DP_API int dp_bn_act_apply(const void* y, const float* scale, const float* shift
   DP_REQUIRE(y && scale && shift && z, DP_ERR_SHAPE, "dp_bn_act_apply: NULL pointer");
   DP_REQUIRE(Cp % 8 == 0 && Cp > 0 && Cp <= 1024 && rows > 0, DP_ERR_ALIGN, "dp_bn_act_apply: bad Cp=%d / rows", Cp);
   const int64_t nvec = rows * (Cp / 8);
-  const int grid = ew_grid(nvec);
-  const size_t sm = 2 * Cp * sizeof(float);
+  const int grid = ew_grid(nvec, Cp / 8);
+  const size_t sm = 0;
   if (dtype == DP_BF16)
     bn_act_apply_kernel<__nv_bfloat16><<<grid, 256, sm, as_stream(stream)>>>(
         (const __nv_bfloat16*)y, scale, shift, slope, (const __nv_bfloat16*)residual, slope_res, (__nv_bfloat16*)z,
@@ -324,7 +362,7 @@ DP_API int dp_bn_bwd_finalize(const float* part, int nparts, int C, int Cp, doub
   DP_REQUIRE(part && coef, DP_ERR_SHAPE, "dp_bn_bwd_finalize: NULL pointer");
   DP_REQUIRE(nparts > 0 && nparts <= DP_MAX_PARTS && C > 0 && Cp >= C && count > 0, DP_ERR_SHAPE,
              "dp_bn_bwd_finalize: bad sizes");
-  bn_bwd_finalize_kernel<<<ceil_div(Cp, 128), 128, 0, as_stream(stream)>>>(part, nparts, C, Cp, count, dgamma, dbeta,
+  bn_bwd_finalize_kernel<<<ceil_div(Cp, FIN_CH), FIN_CH * FIN_PL, 0, as_stream(stream)>>>(part, nparts, C, Cp, count, dgamma, dbeta,
                                                                           coef);
   return check_launch("dp_bn_bwd_finalize");
 }
@@ -338,8 +376,8 @@ DP_API int dp_bn_act_bwd_apply(const void* dz, const void* y, const void* out, c
   DP_REQUIRE(Cp % 8 == 0 && Cp > 0 && Cp <= 1024 && rows > 0, DP_ERR_ALIGN, "dp_bn_act_bwd_apply: bad Cp=%d", Cp);
   DP_REQUIRE(dres == nullptr || out != nullptr, DP_ERR_SHAPE, "dp_bn_act_bwd_apply: dres needs out");
   const int64_t nvec = rows * (Cp / 8);
-  const int grid = ew_grid(nvec);
-  const size_t sm = 6 * Cp * sizeof(float);
+  const int grid = ew_grid(nvec, Cp / 8);
+  const size_t sm = 0;
   if (dtype == DP_BF16)
     bn_act_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, sm, as_stream(stream)>>>(
         (const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, (const __nv_bfloat16*)out, scale, shift, mean, rstd, coef,
@@ -355,7 +393,7 @@ DP_API int dp_add(const void* a, const void* b, void* out, int64_t n, int dtype,
   DP_REQUIRE(a && b && out, DP_ERR_SHAPE, "dp_add: NULL pointer");
   DP_REQUIRE(n > 0 && n % 8 == 0, DP_ERR_ALIGN, "dp_add: n=%lld must be a positive multiple of 8", (long long)n);
   const int64_t nvec = n / 8;
-  const int grid = ew_grid(nvec);
+  const int grid = ew_grid(nvec, 1);
   if (dtype == DP_BF16)
     add_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
                                                                     (__nv_bfloat16*)out, nvec);

@@ -51,7 +51,7 @@ struct TcParams {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmD, const __grid_constant__ TcParams p,
-                      const __nv_bfloat16* __restrict__ addend, float* __restrict__ part) {
+                      const __nv_bfloat16* __restrict__ addend, float* __restrict__ part, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -94,6 +94,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
+    long long w_prod = 0;
+    const long long t_start = dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int r = tile;
       const int n_idx = r % p.n_ntiles; r /= p.n_ntiles;
@@ -104,7 +106,9 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int w0 = tw * p.bw * p.mw, h0 = th * p.bh * p.mh, t0 = tt * p.bt * p.mt;
       for (int l = 0; l < p.nloads; ++l) {
         for (int cb = 0; cb < p.ncblk; ++cb) {
+          const long long c0 = dbg ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (dbg) w_prod += clock64() - c0;
           const uint32_t sa = sbase + (uint32_t)stage * p.stage_bytes;
           mbar_expect_tx(full_bar(stage), (uint32_t)(p.a_box_bytes + p.nsub * p.b_box_bytes));
           tma_load_5d(&tmA, full_bar(stage), sa, cb * p.CB, w0 + p.off_w[l], h0 + p.off_h[l], t0 + p.off_t[l], b);
@@ -117,41 +121,64 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+    if (dbg) { dbg[blockIdx.x * 8 + 0] = w_prod; dbg[blockIdx.x * 8 + 1] = clock64() - t_start; }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
     const uint32_t idesc = make_idesc_bf16(128, p.Ntile, 0, 0);
+    const uint32_t hi = smem_desc_hi((uint32_t)p.sbo_bytes, (uint32_t)p.layout_type);
+    const uint32_t a_sub = (uint32_t)p.sub_row_bytes >> 4, b_sub = (uint32_t)p.b_sub_bytes >> 4;
+    const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
+    const uint32_t lo0 = smem_desc_lo(sbase, 16);
+    const uint32_t b_off0 = stage16 - (uint32_t)p.nsub * b_sub;
+    const int ksteps_full = p.CB >> 4, ncblk = p.ncblk, nsub = p.nsub;
+    const bool leader = elect_one();   // the same lane issues every MMA and every commit
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long w_full = 0, w_te = 0;
+    const long long t_start = dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      long long c0 = dbg ? clock64() : 0;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      if (dbg) w_te += clock64() - c0;
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Ntile);
       uint32_t accumulate = 0;
-      for (int it = 0; it < kiters; ++it) {
-        const int cb = it % p.ncblk;
-        const int ksteps = (cb == p.ncblk - 1) ? p.ksteps_last : (p.CB >> 4);
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        const uint32_t sa = sbase + (uint32_t)stage * p.stage_bytes;
-        for (int s = 0; s < p.nsub; ++s) {
-          const uint32_t a_addr = sa + (uint32_t)(s * p.sub_row_bytes);
-          const uint32_t b_addr = sa + p.stage_bytes - (p.nsub - s) * p.b_sub_bytes;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = make_smem_desc(a_addr + 32u * k, 16, (uint32_t)p.sbo_bytes, (uint32_t)p.layout_type);
-            const uint64_t bdesc = make_smem_desc(b_addr + 32u * k, 16, (uint32_t)p.sbo_bytes, (uint32_t)p.layout_type);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
-            accumulate = 1;
+      for (int l = 0; l < p.nloads; ++l) {
+        for (int cb = 0; cb < ncblk; ++cb) {
+          const int ksteps = (cb == ncblk - 1) ? p.ksteps_last : ksteps_full;
+          c0 = dbg ? clock64() : 0;
+          mbar_wait(full_bar(stage), phase);
+          if (dbg) w_full += clock64() - c0;
+          tc_fence_after();
+          if (leader) {
+            uint32_t a_lo = lo0 + (uint32_t)stage * stage16;
+            uint32_t b_lo = a_lo + b_off0;
+            for (int s = 0; s < nsub; ++s) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < ksteps) {
+                  umma_bf16_lh(tmem_d, a_lo + 2u * k, hi, b_lo + 2u * k, hi, idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              a_lo += a_sub;
+              b_lo += b_sub;
+            }
+            umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
           }
+          __syncwarp();
+          accumulate = 1;
+          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
-        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(tfull_bar(acc));      // accumulator complete -> epilogue
+      if (leader) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (dbg && lane == 0) { dbg[blockIdx.x * 8 + 2] = w_full; dbg[blockIdx.x * 8 + 3] = w_te; dbg[blockIdx.x * 8 + 4] = clock64() - t_start; }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int e = threadIdx.x - (TC_THREADS - TC_EPI);  // 0..127 == accumulator row == TMEM lane
@@ -162,6 +189,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int lw = e % p.bw, lh = (e / p.bw) % p.bh, lt = e / (p.bw * p.bh);
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long w_tf = 0;
+    const long long t_start = dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int r = tile;
       const int n_idx = r % p.n_ntiles; r /= p.n_ntiles;
@@ -176,7 +205,9 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         arow = addend + p.a_off + (int64_t)b * p.a_sb + (int64_t)t * p.a_st + (int64_t)h * p.a_sh + (int64_t)w * p.a_sw +
                n_idx * p.Ntile;
 
+      const long long c0 = dbg ? clock64() : 0;
       mbar_wait(tfull_bar(acc), acc_phase);
+      if (dbg) w_tf += clock64() - c0;
       tc_fence_after();
       if (e == 0) tma_store_wait_read();  // previous tile's TMA store has finished reading the staging tile
       named_bar_sync(1, TC_EPI);
@@ -215,36 +246,49 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         tma_store_commit();
       }
       if (p.has_stats) {
-        const int ncp = p.Ntile >> 1;
-        const int nrg = TC_EPI / ncp;
-        const int cp = e % ncp, rg = e / ncp;
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        // per-channel sum / sum of squares of the bf16 tile: thread = (8-channel vector, row group)
+        const int ncv = p.Ntile >> 3;
+        const int nrg = TC_EPI / ncv;
+        const int cv = e % ncv, rg = e / ncv;
+        float sacc[8], qacc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sacc[j] = 0.f; qacc[j] = 0.f; }
         if (rg < nrg) {
-          const uint32_t* st32 = reinterpret_cast<const uint32_t*>(staging);
           for (int row = rg; row < 128; row += nrg) {
-            uint32_t wv = st32[row * ncp + cp];
-            const float2 fv = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&wv));
-            s0 += fv.x; s1 += fv.y;
-            q0 = fmaf(fv.x, fv.x, q0); q1 = fmaf(fv.y, fv.y, q1);
+            const uint4 u = *reinterpret_cast<const uint4*>(staging + (size_t)row * row_bytes + cv * 16);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 fv = __bfloat1622float2(h[j]);
+              sacc[2 * j] += fv.x; sacc[2 * j + 1] += fv.y;
+              qacc[2 * j] = fmaf(fv.x, fv.x, qacc[2 * j]); qacc[2 * j + 1] = fmaf(fv.y, fv.y, qacc[2 * j + 1]);
+            }
           }
         }
-        scratch[e * 4 + 0] = s0; scratch[e * 4 + 1] = s1; scratch[e * 4 + 2] = q0; scratch[e * 4 + 3] = q1;
-        named_bar_sync(2, TC_EPI);
-        if (e < ncp) {
-          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-          for (int g = 0; g < nrg; ++g) {
-            const float* sp = scratch + (g * ncp + e) * 4;
-            a0 += sp[0]; a1 += sp[1]; b0 += sp[2]; b1 += sp[3];
+        named_bar_sync(2, TC_EPI);                // previous tile's readers of scratch are done
+        if (rg < nrg) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            scratch[(rg * p.Ntile + cv * 8 + j) * 2 + 0] = sacc[j];
+            scratch[(rg * p.Ntile + cv * 8 + j) * 2 + 1] = qacc[j];
           }
-          const int c = n_idx * p.Ntile + 2 * e;
-          stats_sm[c] += a0; stats_sm[c + 1] += a1;
-          stats_sm[p.dC + c] += b0; stats_sm[p.dC + c + 1] += b1;
+        }
+        named_bar_sync(2, TC_EPI);
+        for (int c = e; c < p.Ntile; c += TC_EPI) {
+          float a0 = 0.f, b0 = 0.f;
+          for (int g = 0; g < nrg; ++g) {
+            a0 += scratch[(g * p.Ntile + c) * 2 + 0];
+            b0 += scratch[(g * p.Ntile + c) * 2 + 1];
+          }
+          stats_sm[n_idx * p.Ntile + c] += a0;
+          stats_sm[p.dC + n_idx * p.Ntile + c] += b0;
         }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
     if (e == 0) tma_store_wait_all();
+    if (dbg && e == 0) { dbg[blockIdx.x * 8 + 5] = w_tf; dbg[blockIdx.x * 8 + 6] = clock64() - t_start; }
     if (p.has_stats) {
       named_bar_sync(1, TC_EPI);
       for (int i = e; i < 2 * p.dC; i += TC_EPI) part[(int64_t)blockIdx.x * 2 * p.dC + i] = stats_sm[i];
@@ -346,7 +390,7 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
   p.b_sub_bytes = round_up(p.b_box_bytes, 1024);
   const int staging_bytes = round_up(128 * p.Ntile * 2, 1024);
   const int stats_bytes = round_up(2 * g.dC * 4, 16);
-  const int fixed = staging_bytes + stats_bytes + 2048 + 256 + 1024;
+  const int fixed = staging_bytes + stats_bytes + 8192 + 256 + 1024;
 
   // tile / mode search
   double best = 1e30;
@@ -435,7 +479,7 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
   p.off_staging = stages * p.stage_bytes;
   p.off_stats = p.off_staging + staging_bytes;
   p.off_scratch = p.off_stats + stats_bytes;
-  p.off_bars = p.off_scratch + 2048;
+  p.off_bars = p.off_scratch + 8192;
   int cols = 32;
   while (cols < 2 * p.Ntile) cols <<= 1;
   if (cols > 512) return false;
@@ -532,7 +576,12 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   });
   DP_REQUIRE(attr_err == cudaSuccess, DP_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s",
              cudaGetErrorString(attr_err));
-  tc_gather_gemm_kernel<<<plan.grid, TC_THREADS, plan.smem, s>>>(tmA, tmB, tmD, p, (const __nv_bfloat16*)addend, part);
+  tc_gather_gemm_kernel<<<plan.grid, TC_THREADS, plan.smem, s>>>(tmA, tmB, tmD, p, (const __nv_bfloat16*)addend, part,
+                                                               (g_dbg && g_dbg_slots >= (size_t)plan.grid * 8) ? g_dbg : nullptr);
+  if (getenv("DP_DEBUG_PLAN"))
+    fprintf(stderr, "[tc_gather] dst %dx%dx%dx%d src C=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d CB=%d ncblk=%d Ntile=%d stages=%d stage_bytes=%d a_box=%d tiles=%d grid=%d\n",
+            g.dT, g.dH, g.dW, g.dC, g.sC, g.kt * g.kh * g.kw, p.bw, p.bh, p.bt, p.nloads, p.nsub, p.CB, p.ncblk, p.Ntile, p.num_stages,
+            p.stage_bytes, p.a_box_bytes, p.num_tiles, plan.grid);
   if (nparts != nullptr) *nparts = plan.grid;
   return check_launch("tc_gather_gemm_kernel");
 }

@@ -38,6 +38,10 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 
 int num_sms();
 
+// optional device buffer for per-role cycle counters (dp_set_debug_buffer); nullptr in normal operation
+extern long long* g_dbg;
+extern size_t g_dbg_slots;
+
 // ---- storage-type helpers: 4 consecutive elements <-> float4 ----
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {

@@ -6,6 +6,8 @@ namespace dp {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+long long* g_dbg = nullptr;
+size_t g_dbg_slots = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -33,6 +35,12 @@ DP_API const char* dp_last_error(void) { return dp::g_err; }
 DP_API int dp_num_sms(void) { return dp::num_sms(); }
 
 DP_API unsigned long long dp_launch_count(void) { return dp::g_launches; }
+
+DP_API int dp_set_debug_buffer(void* ptr, size_t bytes) {
+  dp::g_dbg = static_cast<long long*>(ptr);
+  dp::g_dbg_slots = ptr ? bytes / sizeof(long long) : 0;
+  return DP_OK;
+}
 
 DP_API int dp_device_check(void) {
   int dev = 0;

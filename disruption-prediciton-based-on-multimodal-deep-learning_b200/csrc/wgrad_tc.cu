@@ -20,6 +20,7 @@
 #include "dp_common.cuh"
 #include "conv_internal.cuh"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 
@@ -72,7 +73,7 @@ __device__ __forceinline__ WgItem wg_decode(const WgParams& p, int item) {
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD,
-                const __grid_constant__ WgParams p, float* __restrict__ partial) {
+                const __grid_constant__ WgParams p, float* __restrict__ partial, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -110,6 +111,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // ===================== TMA producer =====================
     int xs = 0, ds = 0;
     uint32_t xph = 0, dph = 0;
+    long long w_prod = 0;
+    const long long t_start = dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const WgItem it = wg_decode(p, item);
       const int nD = p.swap ? p.chunksD : it.nchunkM;
@@ -123,14 +126,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int tt = r % p.ntile_t; r /= p.ntile_t;
         const int b = r;
         const int w0 = tw * p.bw, h0 = th * p.bh, t0 = tt * p.bt;
+        long long c0 = dbg ? clock64() : 0;
         mbar_wait(d_empty(ds), dph ^ 1u);
+        if (dbg) w_prod += clock64() - c0;
         const uint32_t da = sbase + (uint32_t)(ds * p.d_slot_bytes);
         mbar_expect_tx(d_full(ds), (uint32_t)(nD * p.d_box_bytes));
         for (int j = 0; j < nD; ++j)
           tma_load_5d(&tmD, d_full(ds), da + (uint32_t)(j * p.d_chunk_bytes), chanD + j * p.cbD, w0, h0, t0, b);
         if (++ds == DS) { ds = 0; dph ^= 1u; }
         for (int l = it.l0; l < it.l1; ++l) {
+          c0 = dbg ? clock64() : 0;
           mbar_wait(x_empty(xs), xph ^ 1u);
+          if (dbg) w_prod += clock64() - c0;
           const uint32_t xa = sbase + (uint32_t)(p.off_x + xs * p.x_slot_bytes);
           mbar_expect_tx(x_full(xs), (uint32_t)(nX * p.x_box_bytes));
           for (int j = 0; j < nX; ++j)
@@ -140,58 +147,82 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+    if (dbg) { dbg[blockIdx.x * 8 + 0] = w_prod; dbg[blockIdx.x * 8 + 1] = clock64() - t_start; }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
     int xs = 0, ds = 0;
     uint32_t xph = 0, dph = 0, tph = 0;
     // operand geometry: U = M side, V = N side
     const int u_rowbytes = p.swap ? p.x_rowbytes : p.d_rowbytes;
     const int v_rowbytes = p.swap ? p.d_rowbytes : p.x_rowbytes;
-    const int u_layout = p.swap ? p.x_layout : p.d_layout;
-    const int v_layout = p.swap ? p.d_layout : p.x_layout;
-    const int u_lbo = p.swap ? p.x_chunk_bytes : p.d_chunk_bytes;
-    const int v_lbo = p.swap ? p.d_chunk_bytes : p.x_chunk_bytes;
+    const uint32_t u_hi = smem_desc_hi((uint32_t)(8 * u_rowbytes), (uint32_t)(p.swap ? p.x_layout : p.d_layout));
+    const uint32_t v_hi = smem_desc_hi((uint32_t)(8 * v_rowbytes), (uint32_t)(p.swap ? p.d_layout : p.x_layout));
+    const uint32_t u_lbo = (uint32_t)(p.swap ? p.x_chunk_bytes : p.d_chunk_bytes);
+    const uint32_t v_lbo = (uint32_t)(p.swap ? p.d_chunk_bytes : p.x_chunk_bytes);
+    const uint32_t u_step = (uint32_t)(16 * u_rowbytes) >> 4, v_step = (uint32_t)(16 * v_rowbytes) >> 4;
+    const uint32_t x_shift16 = (uint32_t)p.x_shift_bytes >> 4;
+    const uint32_t d_lo0 = smem_desc_lo(sbase, p.swap ? v_lbo : u_lbo);
+    const uint32_t x_lo0 = smem_desc_lo(sbase + (uint32_t)p.off_x, p.swap ? u_lbo : v_lbo);
+    const uint32_t d_slot16 = (uint32_t)p.d_slot_bytes >> 4, x_slot16 = (uint32_t)p.x_slot_bytes >> 4;
+    const int nsub = p.nsub;
+    const uint32_t N = (uint32_t)p.N;
+    const bool leader = elect_one();
+    long long w_full = 0, w_te = 0;
+    const long long t_start = dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const WgItem it = wg_decode(p, item);
       const uint32_t idesc = make_idesc_bf16(it.Mi, p.N, 1, 1);
+      long long c0 = dbg ? clock64() : 0;
       mbar_wait(tempty, tph ^ 1u);
+      if (dbg) w_te += clock64() - c0;
       tc_fence_after();
       for (int tile = it.tile0; tile < it.tile1; ++tile) {
+        c0 = dbg ? clock64() : 0;
         mbar_wait(d_full(ds), dph);
+        if (dbg) w_full += clock64() - c0;
         tc_fence_after();
-        const uint32_t da = sbase + (uint32_t)(ds * p.d_slot_bytes);
+        const uint32_t d_lo = d_lo0 + (uint32_t)ds * d_slot16;
+        const uint32_t first = (tile != it.tile0) ? 1u : 0u;
+        uint32_t tmem_d = tmem_base;
         for (int l = it.l0; l < it.l1; ++l) {
+          c0 = dbg ? clock64() : 0;
           mbar_wait(x_full(xs), xph);
+          if (dbg) w_full += clock64() - c0;
           tc_fence_after();
-          const uint32_t xa = sbase + (uint32_t)(p.off_x + xs * p.x_slot_bytes);
-          for (int s = 0; s < p.nsub; ++s) {
-            const uint32_t xs_addr = xa + (uint32_t)(s * p.x_shift_bytes);
-            const uint32_t u_addr = p.swap ? xs_addr : da;
-            const uint32_t v_addr = p.swap ? da : xs_addr;
-            const uint32_t tmem_d = tmem_base + (uint32_t)(((l - it.l0) * p.nsub + s) * p.N);
+          if (leader) {
+            uint32_t x_lo = x_lo0 + (uint32_t)xs * x_slot16;
+            for (int s = 0; s < nsub; ++s) {
+              const uint32_t u_lo = p.swap ? x_lo : d_lo, v_lo = p.swap ? d_lo : x_lo;
+              umma_bf16_lh(tmem_d, u_lo, u_hi, v_lo, v_hi, idesc, first);
 #pragma unroll
-            for (int ks = 0; ks < WG_P / 16; ++ks) {
-              const uint64_t adesc = make_smem_desc(u_addr + (uint32_t)(ks * 16 * u_rowbytes), (uint32_t)u_lbo,
-                                                    (uint32_t)(8 * u_rowbytes), (uint32_t)u_layout);
-              const uint64_t bdesc = make_smem_desc(v_addr + (uint32_t)(ks * 16 * v_rowbytes), (uint32_t)v_lbo,
-                                                    (uint32_t)(8 * v_rowbytes), (uint32_t)v_layout);
-              umma_bf16(tmem_d, adesc, bdesc, idesc, (tile != it.tile0 || ks != 0) ? 1u : 0u);
+              for (int ks = 1; ks < WG_P / 16; ++ks)
+                umma_bf16_lh(tmem_d, u_lo + ks * u_step, u_hi, v_lo + ks * v_step, v_hi, idesc, 1u);
+              x_lo += x_shift16;
+              tmem_d += N;
             }
+            umma_commit(x_empty(xs));
+          } else {
+            tmem_d += N * (uint32_t)nsub;
           }
-          umma_commit(x_empty(xs));
+          __syncwarp();
           if (++xs == XS) { xs = 0; xph ^= 1u; }
         }
-        umma_commit(d_empty(ds));
+        if (leader) umma_commit(d_empty(ds));
+        __syncwarp();
         if (++ds == DS) { ds = 0; dph ^= 1u; }
       }
-      umma_commit(tfull);
+      if (leader) umma_commit(tfull);
+      __syncwarp();
       tph ^= 1u;
     }
+    if (dbg && lane == 0) { dbg[blockIdx.x * 8 + 2] = w_full; dbg[blockIdx.x * 8 + 3] = w_te; dbg[blockIdx.x * 8 + 4] = clock64() - t_start; }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> fp32 partial =====================
     const int q = warp & 3;
     uint32_t tph = 0;
     const int64_t split_stride = (int64_t)p.Kp * p.taps * p.Cp;
+    long long w_tf = 0;
+    const long long t_start = dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const WgItem it = wg_decode(p, item);
       const int row = it.Mi == 128 ? (q * 32 + lane) : (q * 16 + lane);
@@ -199,7 +230,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int u = 128 * it.mtile + row;                // channel index on the M side
       const bool valid = lane_ok && u < (p.swap ? p.Cp : p.Kp);
       float* base = partial + (int64_t)it.split * split_stride;
+      const long long c0 = dbg ? clock64() : 0;
       mbar_wait(tfull, tph);
+      if (dbg) w_tf += clock64() - c0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int l = it.l0; l < it.l1; ++l) {
@@ -229,6 +262,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_arrive(tempty);
       tph ^= 1u;
     }
+    if (dbg && threadIdx.x == WG_THREADS - WG_EPI) { dbg[blockIdx.x * 8 + 5] = w_tf; dbg[blockIdx.x * 8 + 6] = clock64() - t_start; }
   }
 
   tc_fence_before();
@@ -489,7 +523,12 @@ int tc_conv_wgrad_view(const dp_conv_desc* d, const long long* xstrides, const v
   });
   DP_REQUIRE(attr_err == cudaSuccess, DP_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s",
              cudaGetErrorString(attr_err));
-  wgrad_tc_kernel<<<plan.grid, WG_THREADS, plan.smem, s>>>(tmX, tmD, p, (float*)ws);
+  wgrad_tc_kernel<<<plan.grid, WG_THREADS, plan.smem, s>>>(tmX, tmD, p, (float*)ws,
+                                                           (g_dbg && g_dbg_slots >= (size_t)plan.grid * 8) ? g_dbg : nullptr);
+  if (getenv("DP_DEBUG_PLAN"))
+    fprintf(stderr, "[tc_wgrad] out %dx%dx%d Kp=%d Cp=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d swap=%d N=%d n_mt=%d n_tg=%d lpg=%d cbX=%d cbD=%d xslots=%d dslots=%d xslot=%d dslot=%d nsplit=%d tiles/split=%d grid=%d\n",
+            d->To, d->Ho, d->Wo, d->Kp, d->Cp, p.taps, p.bw, p.bh, p.bt, p.nloads, p.nsub, p.swap, p.N, p.n_mt, p.n_tg, p.lpg, p.cbX,
+            p.cbD, p.x_slots, p.d_slots, p.x_slot_bytes, p.d_slot_bytes, p.nsplit, p.tiles_per_split, plan.grid);
   rc = check_launch("wgrad_tc_kernel");
   if (rc != DP_OK) return rc;
   return wgrad_reduce_launch((const float*)ws, dw, p.nsplit, d->K, d->C, d->Kp, d->Cp, p.taps, s);

@@ -75,6 +75,9 @@ unsigned long long dp_launch_count(void);
 /* tuning / debug switches: "tc_enable", "tc_halo", "tc_strided", "tc_max_stages", "wg_enable", "wg_halo" */
 int         dp_set_option(const char* name, int value);
 int         dp_get_option(const char* name);
+/* development aid: device buffer (>= 8 int64 per CTA) receiving per-role wait/busy cycle counters of the tcgen05
+ * kernels; NULL switches it off (the default) */
+int         dp_set_debug_buffer(void* ptr, size_t bytes);
 
 /* ---- layout (replaces the implicit NCDHW contract of DatasetForVideo, src/dataset.py:229-230) ---- */
 int dp_ncdhw_f32_to_ndhwc(const float* src, void* dst, int B, int C, int Cp, int T, int H, int W,
