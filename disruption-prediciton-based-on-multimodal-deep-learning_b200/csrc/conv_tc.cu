@@ -27,8 +27,8 @@ namespace dp {
 using namespace ptx;
 
 constexpr int TC_MAX_LOADS = 49;
-constexpr int TC_THREADS = 256;
-constexpr int TC_EPI = 128;
+constexpr int TC_THREADS = 384;   // warps: 0 TMA loads, 1 MMA, 2 TMEM alloc, 3 TMA stores, 4-11 epilogue
+constexpr int TC_EPI = 256;       // two epilogue warps per TMEM lane quadrant, each drains half of the columns
 constexpr int TC_SMEM_MAX = 232448;  // 227 KB opt-in limit per CTA
 
 struct TcParams {
@@ -40,12 +40,39 @@ struct TcParams {
   int sub_row_bytes, tap_sub_stride, red_C;
   int Ntile;
   int a_box_bytes, b_box_bytes, b_sub_bytes, stage_bytes, num_stages;
-  int off_staging, off_stats, off_scratch, off_bars;
+  int w_resident, off_wgt;  // all weight blocks loaded once per CTA instead of once per stage
+  int mma_stats, stat_M, acc_bufs;  // BN statistics accumulated in TMEM by the tensor core
+  // staging tile (epilogue -> TMA store, and B operand of the statistics MMAs): chunks of cw channels, swizzled
+  int cw_shift;  // log2(cw) for the chunked layout, -1 for one unswizzled chunk of Ntile channels
+  int cw, st_chunks, st_rowbytes, st_chunk_bytes, st_buf_bytes, st_bufs, st_mask, st_layout;
+  int off_staging, off_ones, off_stats, off_scratch, off_bars;
   int tmem_cols, layout_type, sbo_bytes;
   int has_stats, has_addend;
   long long a_off, a_sw, a_sh, a_st, a_sb;  // addend view: element offset / strides of (w,h,t,b) in the dst tensor
   signed char off_w[TC_MAX_LOADS], off_h[TC_MAX_LOADS], off_t[TC_MAX_LOADS];
   short tap0[TC_MAX_LOADS];
+};
+
+// Tile coordinates (n, w, h, t, b) of tile = blockIdx.x + i * gridDim.x, advanced by mixed-radix addition of the
+// constant stride: no division in the per-tile path.
+struct TileIter {
+  int n, w, h, t, b;       // current coordinates
+  int dn, dw, dh, dt, db;  // stride decomposition
+  int Rn, Rw, Rh, Rt;
+  __device__ __forceinline__ void init(const TcParams& p, int start, int stride) {
+    Rn = p.n_ntiles; Rw = p.ntile_w; Rh = p.ntile_h; Rt = p.ntile_t;
+    int r = start;
+    n = r % Rn; r /= Rn; w = r % Rw; r /= Rw; h = r % Rh; r /= Rh; t = r % Rt; b = r / Rt;
+    r = stride;
+    dn = r % Rn; r /= Rn; dw = r % Rw; r /= Rw; dh = r % Rh; r /= Rh; dt = r % Rt; db = r / Rt;
+  }
+  __device__ __forceinline__ void next() {
+    n += dn; int c = n >= Rn; n -= c ? Rn : 0;
+    w += dw + c; c = w >= Rw; w -= c ? Rw : 0;
+    h += dh + c; c = h >= Rh; h -= c ? Rh : 0;
+    t += dt + c; c = t >= Rt; t -= c ? Rt : 0;
+    b += db + c;
+  }
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -64,7 +91,12 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   auto empty_bar = [&](int i) { return bars + 8u * (S + i); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.off_bars + 8 * (2 * S + 4));
+  const uint32_t wbar = bars + 8u * (2 * S + 4);
+  auto sready_bar = [&](int b) { return bars + 8u * (2 * S + 5 + b); };
+  auto sdone_bar = [&](int b) { return bars + 8u * (2 * S + 7 + b); };
+  auto sfree_bar = [&](int b) { return bars + 8u * (2 * S + 9 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 11);
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.off_bars + 8 * (2 * S + 11));
   float* stats_sm = reinterpret_cast<float*>(sm + p.off_stats);
   float* scratch = reinterpret_cast<float*>(sm + p.off_scratch);
 
@@ -73,22 +105,32 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
     for (int i = 0; i < S; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI);
+      mbar_init(sready_bar(a), TC_EPI); mbar_init(sdone_bar(a), 1); mbar_init(sfree_bar(a), 1);
+    }
+    mbar_init(wbar, 1);
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(sbase + p.off_bars + 8 * (2 * S + 4), (uint32_t)p.tmem_cols);
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
   if (threadIdx.x >= TC_THREADS - TC_EPI) {
-    for (int i = threadIdx.x - (TC_THREADS - TC_EPI); i < 2 * p.dC; i += TC_EPI) stats_sm[i] = 0.f;
+    const int e0 = threadIdx.x - (TC_THREADS - TC_EPI);
+    if (p.has_stats && !p.mma_stats)
+      for (int i = e0; i < 2 * p.dC; i += TC_EPI) stats_sm[i] = 0.f;
+    if (p.mma_stats) {   // the all-ones A operand of the column-sum MMA (any canonical layout: every element is 1)
+      uint32_t* ones = reinterpret_cast<uint32_t*>(sm + p.off_ones);
+      for (int i = e0; i < 512; i += TC_EPI) ones[i] = 0x3F803F80u;
+      fence_proxy_async_smem();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-
-  const int kiters = p.nloads * p.ncblk;
+  const uint32_t col_g = (uint32_t)(p.acc_bufs * p.Ntile), col_s = col_g + (uint32_t)p.Ntile;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -96,26 +138,34 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint32_t phase = 0;
     long long w_prod = 0;
     const long long t_start = dbg ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int r = tile;
-      const int n_idx = r % p.n_ntiles; r /= p.n_ntiles;
-      const int tw = r % p.ntile_w; r /= p.ntile_w;
-      const int th = r % p.ntile_h; r /= p.ntile_h;
-      const int tt = r % p.ntile_t; r /= p.ntile_t;
-      const int b = r;
-      const int w0 = tw * p.bw * p.mw, h0 = th * p.bh * p.mh, t0 = tt * p.bt * p.mt;
+    if (p.w_resident) {
+      mbar_expect_tx(wbar, (uint32_t)(p.nloads * p.nsub * p.ncblk * p.b_box_bytes));
+      for (int l = 0; l < p.nloads; ++l)
+        for (int s = 0; s < p.nsub; ++s)
+          for (int cb = 0; cb < p.ncblk; ++cb)
+            tma_load_2d(&tmB, wbar, sbase + (uint32_t)(p.off_wgt + ((l * p.nsub + s) * p.ncblk + cb) * p.b_sub_bytes),
+                        (p.tap0[l] + s * p.tap_sub_stride) * p.red_C + cb * p.CB, 0);
+    }
+    const uint32_t tx = (uint32_t)(p.a_box_bytes + (p.w_resident ? 0 : p.nsub * p.b_box_bytes));
+    TileIter ti;
+    ti.init(p, blockIdx.x, gridDim.x);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti.next()) {
+      const int n_idx = ti.n, b = ti.b;
+      const int w0 = ti.w * p.bw * p.mw, h0 = ti.h * p.bh * p.mh, t0 = ti.t * p.bt * p.mt;
       for (int l = 0; l < p.nloads; ++l) {
         for (int cb = 0; cb < p.ncblk; ++cb) {
           const long long c0 = dbg ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (dbg) w_prod += clock64() - c0;
           const uint32_t sa = sbase + (uint32_t)stage * p.stage_bytes;
-          mbar_expect_tx(full_bar(stage), (uint32_t)(p.a_box_bytes + p.nsub * p.b_box_bytes));
+          mbar_expect_tx(full_bar(stage), tx);
           tma_load_5d(&tmA, full_bar(stage), sa, cb * p.CB, w0 + p.off_w[l], h0 + p.off_h[l], t0 + p.off_t[l], b);
-          for (int s = 0; s < p.nsub; ++s) {
-            const int tap = p.tap0[l] + s * p.tap_sub_stride;
-            tma_load_2d(&tmB, full_bar(stage), sa + p.stage_bytes - (p.nsub - s) * p.b_sub_bytes,
-                        tap * p.red_C + cb * p.CB, n_idx * p.Ntile);
+          if (!p.w_resident) {
+            for (int s = 0; s < p.nsub; ++s) {
+              const int tap = p.tap0[l] + s * p.tap_sub_stride;
+              tma_load_2d(&tmB, full_bar(stage), sa + p.stage_bytes - (p.nsub - s) * p.b_sub_bytes,
+                          tap * p.red_C + cb * p.CB, n_idx * p.Ntile);
+            }
           }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -129,22 +179,50 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t a_sub = (uint32_t)p.sub_row_bytes >> 4, b_sub = (uint32_t)p.b_sub_bytes >> 4;
     const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
     const uint32_t lo0 = smem_desc_lo(sbase, 16);
+    const uint32_t wlo0 = smem_desc_lo(sbase + (uint32_t)p.off_wgt, 16);
     const uint32_t b_off0 = stage16 - (uint32_t)p.nsub * b_sub;
     const int ksteps_full = p.CB >> 4, ncblk = p.ncblk, nsub = p.nsub;
+    const bool resident = p.w_resident != 0;
+    const uint32_t b_step = resident ? (uint32_t)ncblk * b_sub : b_sub;
+    // statistics MMAs: D_g += Y^T Y (diagonal = sum of squares), D_s += 1^T Y (column sums); Y = staged bf16 tile
+    const uint32_t st_hi = smem_desc_hi((uint32_t)(8 * p.st_rowbytes), (uint32_t)p.st_layout);
+    const uint32_t st_lo0 = smem_desc_lo(sbase + (uint32_t)p.off_staging, (uint32_t)p.st_chunk_bytes);
+    const uint32_t st_step = (uint32_t)(16 * p.st_rowbytes) >> 4, st_buf16 = (uint32_t)p.st_buf_bytes >> 4;
+    const uint32_t ones_lo = smem_desc_lo(sbase + (uint32_t)p.off_ones, 128), ones_hi = smem_desc_hi(256, 0);
+    const uint32_t idesc_g = make_idesc_bf16(p.stat_M, p.Ntile, 1, 1), idesc_s = make_idesc_bf16(64, p.Ntile, 0, 1);
     const bool leader = elect_one();   // the same lane issues every MMA and every commit
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int it = 0;
     long long w_full = 0, w_te = 0;
     const long long t_start = dbg ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    auto issue_stats = [&](int j) {
+      const int buf = j % p.st_bufs;
+      mbar_wait(sready_bar(buf), (uint32_t)((j / p.st_bufs) & 1));
+      tc_fence_after();
+      if (leader) {
+        const uint32_t y_lo = st_lo0 + (uint32_t)buf * st_buf16;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t accum = (j > 0 || ks > 0) ? 1u : 0u;
+          umma_bf16_lh(tmem_base + col_g, y_lo + ks * st_step, st_hi, y_lo + ks * st_step, st_hi, idesc_g, accum);
+          umma_bf16_lh(tmem_base + col_s, ones_lo, ones_hi, y_lo + ks * st_step, st_hi, idesc_s, accum);
+        }
+        umma_commit(sdone_bar(buf));
+      }
+      __syncwarp();
+    };
+    if (resident) { mbar_wait(wbar, 0u); tc_fence_after(); }
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       long long c0 = dbg ? clock64() : 0;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       if (dbg) w_te += clock64() - c0;
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Ntile);
       uint32_t accumulate = 0;
+      uint32_t w_lo = wlo0;
       for (int l = 0; l < p.nloads; ++l) {
         for (int cb = 0; cb < ncblk; ++cb) {
           const int ksteps = (cb == ncblk - 1) ? p.ksteps_last : ksteps_full;
@@ -154,7 +232,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tc_fence_after();
           if (leader) {
             uint32_t a_lo = lo0 + (uint32_t)stage * stage16;
-            uint32_t b_lo = a_lo + b_off0;
+            uint32_t b_lo = resident ? (w_lo + (uint32_t)cb * b_sub) : (a_lo + b_off0);
             for (int s = 0; s < nsub; ++s) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -164,7 +242,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
               }
               a_lo += a_sub;
-              b_lo += b_sub;
+              b_lo += b_step;
             }
             umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
           }
@@ -172,55 +250,91 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           accumulate = 1;
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
+        w_lo += (uint32_t)(nsub * ncblk) * b_sub;
       }
       if (leader) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
       __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1u; }
+      if (p.mma_stats && it > 0) issue_stats(it - 1);
     }
+    if (p.mma_stats && it > 0) issue_stats(it - 1);
     if (dbg && lane == 0) { dbg[blockIdx.x * 8 + 2] = w_full; dbg[blockIdx.x * 8 + 3] = w_te; dbg[blockIdx.x * 8 + 4] = clock64() - t_start; }
+  } else if (warp == 3 && lane == 0) {
+    // ===================== TMA store issuer: staged tile -> global, off the epilogue's critical path ==========
+    const int nst = (p.Ntile + p.cw - 1) / p.cw;
+    int it = 0, prev_buf = -1;
+    TileIter ti;
+    ti.init(p, blockIdx.x, gridDim.x);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, ti.next()) {
+      const int n_idx = ti.n, tw = ti.w, th = ti.h, tt = ti.t, b = ti.b;
+      const int buf = it % p.st_bufs;
+      mbar_wait(sready_bar(buf), (uint32_t)((it / p.st_bufs) & 1));
+      const uint32_t staging_s = sbase + (uint32_t)(p.off_staging + buf * p.st_buf_bytes);
+      for (int ch = 0; ch < nst; ++ch)
+        tma_store_5d(&tmD, staging_s + (uint32_t)(ch * p.st_chunk_bytes), n_idx * p.Ntile + ch * p.cw, tw * p.bw,
+                     th * p.bh, tt * p.bt, b);
+      tma_store_commit();
+      if (p.st_bufs == 2) {
+        tma_store_wait_read1();                       // the previous tile's store has finished reading its buffer
+        if (prev_buf >= 0) mbar_arrive(sfree_bar(prev_buf));
+        prev_buf = buf;
+      } else {
+        tma_store_wait_read();
+        mbar_arrive(sfree_bar(buf));
+      }
+    }
+    tma_store_wait_all();
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int e = threadIdx.x - (TC_THREADS - TC_EPI);  // 0..127 == accumulator row == TMEM lane
-    const int q = warp & 3;
-    uint8_t* staging = sm + p.off_staging;
-    const uint32_t staging_s = sbase + p.off_staging;
-    const int row_bytes = p.Ntile * 2;
+    // ===================== epilogue: TMEM -> bf16 -> swizzled staging tile =====================
+    const int et = threadIdx.x - (TC_THREADS - TC_EPI);  // 0..255
+    const int q = warp & 3;                              // TMEM lane quadrant this warp may access
+    const int e = q * 32 + lane;                         // accumulator row == TMEM lane == pixel of the tile
+    const int chalf = (warp - 4) >> 2;                   // which half of the columns this warp drains
+    const int csplit = ((p.Ntile >> 4) + 1) / 2 * 16;    // columns [0,csplit) -> half 0, [csplit,Ntile) -> half 1
+    const int cbeg = chalf ? csplit : 0, cend = chalf ? p.Ntile : csplit;
     const int lw = e % p.bw, lh = (e / p.bw) % p.bh, lt = e / (p.bw * p.bh);
+    const uint32_t row_off = (uint32_t)(e * p.st_rowbytes);
+    const uint32_t st_mask = (uint32_t)p.st_mask;
+    const bool legacy_stats = p.has_stats && !p.mma_stats;
     int acc = 0;
     uint32_t acc_phase = 0;
-    long long w_tf = 0;
+    int it = 0;
+    long long w_tf = 0, w_a = 0, w_b = 0, w_c = 0, w_d = 0;
     const long long t_start = dbg ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int r = tile;
-      const int n_idx = r % p.n_ntiles; r /= p.n_ntiles;
-      const int tw = r % p.ntile_w; r /= p.ntile_w;
-      const int th = r % p.ntile_h; r /= p.ntile_h;
-      const int tt = r % p.ntile_t; r /= p.ntile_t;
-      const int b = r;
-      const int w = tw * p.bw + lw, h = th * p.bh + lh, t = tt * p.bt + lt;
+    TileIter ti;
+    ti.init(p, blockIdx.x, gridDim.x);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, ti.next()) {
+      const int n_idx = ti.n, b = ti.b;
+      const int w = ti.w * p.bw + lw, h = ti.h * p.bh + lh, t = ti.t * p.bt + lt;
       const bool valid = (w < p.dW) && (h < p.dH) && (t < p.dT);
       const __nv_bfloat16* arow = nullptr;
       if (p.has_addend && valid)
         arow = addend + p.a_off + (int64_t)b * p.a_sb + (int64_t)t * p.a_st + (int64_t)h * p.a_sh + (int64_t)w * p.a_sw +
                n_idx * p.Ntile;
+      const int buf = it % p.st_bufs;
+      uint8_t* staging = sm + p.off_staging + buf * p.st_buf_bytes;
 
       const long long c0 = dbg ? clock64() : 0;
       mbar_wait(tfull_bar(acc), acc_phase);
       if (dbg) w_tf += clock64() - c0;
+      long long c1 = dbg ? clock64() : 0;
       tc_fence_after();
-      if (e == 0) tma_store_wait_read();  // previous tile's TMA store has finished reading the staging tile
-      named_bar_sync(1, TC_EPI);
+      // the staging buffer is free once the TMA store issued st_bufs tiles ago has read it and (statistics) the
+      // MMAs over it have retired
+      if (it >= p.st_bufs) {
+        const uint32_t par = (uint32_t)(((it / p.st_bufs) - 1) & 1);
+        mbar_wait(sfree_bar(buf), par);
+        if (p.mma_stats) mbar_wait(sdone_bar(buf), par);
+      }
+      if (dbg) { const long long c2 = clock64(); w_a += c2 - c1; c1 = c2; }
 
       const uint32_t taddr = tmem_base + (uint32_t)(acc * p.Ntile) + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.Ntile; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
+      auto emit16 = [&](const uint32_t* v, int c) {   // 16 accumulator columns starting at channel c of this tile
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = valid ? __uint_as_float(v[j]) : 0.f;
         if (arow != nullptr) {
-          const f8 a0 = ld8(arow + c0), a1 = ld8(arow + c0 + 8);
+          const f8 a0 = ld8(arow + c), a1 = ld8(arow + c + 8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { f[j] += a0.v[j]; f[8 + j] += a1.v[j]; }
         }
@@ -232,34 +346,52 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           h0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
           h1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
         }
-        uint4* dstp = reinterpret_cast<uint4*>(staging + (size_t)e * row_bytes + c0 * 2);
-        dstp[0] = o0;
-        dstp[1] = o1;
+        const int chunk = p.cw_shift >= 0 ? (c >> p.cw_shift) : 0;
+        uint32_t off = row_off + (uint32_t)((c - chunk * p.cw) * 2);
+        uint8_t* cbase = staging + chunk * p.st_chunk_bytes;
+        const uint32_t off0 = off ^ (((off >> 7) & st_mask) << 4);
+        off += 16u;
+        const uint32_t off1 = off ^ (((off >> 7) & st_mask) << 4);
+        *reinterpret_cast<uint4*>(cbase + off0) = o0;
+        *reinterpret_cast<uint4*>(cbase + off1) = o1;
+      };
+      for (int c0c = cbeg; c0c < cend; c0c += 64) {
+        // up to 64 columns in flight per wait (column counts are multiples of 16)
+        uint32_t va[32], vb[32];
+        const int rem = cend - c0c;
+        if (rem >= 32) tmem_ld32_nowait(taddr + (uint32_t)c0c, va); else tmem_ld16_nowait(taddr + (uint32_t)c0c, va);
+        if (rem >= 64) tmem_ld32_nowait(taddr + (uint32_t)c0c + 32u, vb);
+        else if (rem >= 48) tmem_ld16_nowait(taddr + (uint32_t)c0c + 32u, vb);
+        tmem_wait_ld16(va); tmem_wait_ld16(va + 16); tmem_wait_ld16(vb); tmem_wait_ld16(vb + 16);
+        emit16(va, c0c);
+        if (rem >= 32) emit16(va + 16, c0c + 16);
+        if (rem >= 48) emit16(vb, c0c + 32);
+        if (rem >= 64) emit16(vb + 16, c0c + 48);
       }
-      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      if (dbg) { const long long c2 = clock64(); w_b += c2 - c1; c1 = c2; }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp; publish the staged tile to the async proxy
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       fence_proxy_async_smem();
-      named_bar_sync(1, TC_EPI);
-      if (e == 0) {
-        tma_store_5d(&tmD, staging_s, n_idx * p.Ntile, tw * p.bw, th * p.bh, tt * p.bt, b);
-        tma_store_commit();
-      }
-      if (p.has_stats) {
-        // per-channel sum / sum of squares of the bf16 tile: thread = (8-channel vector, row group)
+      if (legacy_stats) named_bar_sync(1, TC_EPI);
+      mbar_arrive(sready_bar(buf));     // 128 arrivals: TMA-store warp (and the statistics MMAs) may read the tile
+      if (dbg) { const long long c2 = clock64(); w_c += c2 - c1; c1 = c2; }
+      if (legacy_stats) {
+        // fallback (N tiles > 1): per-channel sum / sum of squares of the bf16 tile from the (unswizzled) staging tile
+        const int row_bytes = p.st_rowbytes;
         const int ncv = p.Ntile >> 3;
         const int nrg = TC_EPI / ncv;
-        const int cv = e % ncv, rg = e / ncv;
+        const int cv = et % ncv, rg = et / ncv;
         float sacc[8], qacc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sacc[j] = 0.f; qacc[j] = 0.f; }
         if (rg < nrg) {
           for (int row = rg; row < 128; row += nrg) {
             const uint4 u = *reinterpret_cast<const uint4*>(staging + (size_t)row * row_bytes + cv * 16);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 fv = __bfloat1622float2(h[j]);
+              const float2 fv = __bfloat1622float2(hh[j]);
               sacc[2 * j] += fv.x; sacc[2 * j + 1] += fv.y;
               qacc[2 * j] = fmaf(fv.x, fv.x, qacc[2 * j]); qacc[2 * j + 1] = fmaf(fv.y, fv.y, qacc[2 * j + 1]);
             }
@@ -274,7 +406,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
         }
         named_bar_sync(2, TC_EPI);
-        for (int c = e; c < p.Ntile; c += TC_EPI) {
+        for (int c = et; c < p.Ntile; c += TC_EPI) {
           float a0 = 0.f, b0 = 0.f;
           for (int g = 0; g < nrg; ++g) {
             a0 += scratch[(g * p.Ntile + c) * 2 + 0];
@@ -283,15 +415,53 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           stats_sm[n_idx * p.Ntile + c] += a0;
           stats_sm[p.dC + n_idx * p.Ntile + c] += b0;
         }
+        // legacy statistics read the tile in place: it may only be re-used (sfree) after these reads; with one
+        // staging buffer the next tile's drain waits for sfree, which the store warp signals after ITS read, and the
+        // named barriers above order the readers before any thread can pass the next sready arrival
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (dbg) { const long long c2 = clock64(); w_d += c2 - c1; c1 = c2; }
+      if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1u; }
     }
-    if (e == 0) tma_store_wait_all();
-    if (dbg && e == 0) { dbg[blockIdx.x * 8 + 5] = w_tf; dbg[blockIdx.x * 8 + 6] = clock64() - t_start; }
-    if (p.has_stats) {
+    if (dbg && et == 0) {
+      dbg[blockIdx.x * 8 + 5] = w_tf; dbg[blockIdx.x * 8 + 6] = clock64() - t_start;
+      long long* d2 = dbg + 148 * 8 + blockIdx.x * 8;
+      d2[0] = w_a; d2[1] = w_b; d2[2] = w_c; d2[3] = w_d;
+    }
+    if (legacy_stats) {
       named_bar_sync(1, TC_EPI);
-      for (int i = e; i < 2 * p.dC; i += TC_EPI) part[(int64_t)blockIdx.x * 2 * p.dC + i] = stats_sm[i];
+      for (int i = et; i < 2 * p.dC; i += TC_EPI) part[(int64_t)blockIdx.x * 2 * p.dC + i] = stats_sm[i];
+    }
+    if (p.mma_stats && chalf == 0) {
+      // all statistics MMAs of this CTA have retired once the last staged tile's are done
+      const int last = it - 1;
+      mbar_wait(sdone_bar(last % p.st_bufs), (uint32_t)((last / p.st_bufs) & 1));
+      tc_fence_after();
+      float* prow = part + (int64_t)blockIdx.x * 2 * p.dC;
+      const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+      if (q == 0) {   // column sums: every row of D_s is the same, row 0 lives in TMEM lane 0
+        for (int n0 = 0; n0 < p.Ntile; n0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + col_s + (uint32_t)n0, v);
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) prow[n0 + j] = __uint_as_float(v[j]);
+          }
+        }
+      }
+      // sums of squares: diagonal of D_g.  M=128: channel m in lane m; M=64: channel i in lane (i%16) + 32*(i/16)
+      const int per_warp = p.stat_M == 128 ? 32 : 16;
+      const int cbase = q * per_warp;
+      if (cbase < p.Ntile) {
+        float val = 0.f;
+        for (int n0 = 0; n0 < per_warp; n0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + lane_base + col_g + (uint32_t)(cbase + n0), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (lane == n0 + j) val = __uint_as_float(v[j]);
+        }
+        if (lane < per_warp && cbase + lane < p.Ntile) prow[p.dC + cbase + lane] = val;
+      }
     }
   }
 
@@ -323,13 +493,17 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1;
+static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2;
 int tc_option(const char* name, int value, bool set) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_opt_halo;
   else if (!strcmp(name, "tc_strided")) slot = &g_opt_strided;
   else if (!strcmp(name, "tc_max_stages")) slot = &g_opt_max_stages;
   else if (!strcmp(name, "tc_enable")) slot = &g_opt_tc;
+  else if (!strcmp(name, "tc_mma_stats")) slot = &g_opt_mma_stats;
+  else if (!strcmp(name, "tc_resident")) slot = &g_opt_resident;
+  else if (!strcmp(name, "tc_chunked")) slot = &g_opt_chunked;
+  else if (!strcmp(name, "tc_st_bufs")) slot = &g_opt_st_bufs;
   if (slot == nullptr) return -1;
   if (set) *slot = value;
   return *slot;
@@ -388,9 +562,33 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
   p.red_C = g.sC;
   p.b_box_bytes = p.Ntile * rowbytes;
   p.b_sub_bytes = round_up(p.b_box_bytes, 1024);
-  const int staging_bytes = round_up(128 * p.Ntile * 2, 1024);
+  // staging layout / statistics mode / resident weights
+  const int used_taps = taps;
+  p.has_stats = has_stats ? 1 : 0;
+  p.mma_stats = (has_stats && g_opt_mma_stats && p.n_ntiles == 1 && p.Ntile <= 128) ? 1 : 0;
+  const bool chunked = p.n_ntiles == 1 && (p.mma_stats || (!has_stats && g_opt_chunked));
+  if (chunked) {
+    p.cw = p.Ntile > 32 ? 64 : (p.Ntile == 32 ? 32 : 16);
+    p.st_mask = p.cw == 64 ? 7 : (p.cw == 32 ? 3 : 1);
+    p.st_layout = p.cw == 64 ? 2 : (p.cw == 32 ? 4 : 6);
+  } else {
+    p.cw = p.Ntile; p.st_mask = 0; p.st_layout = 0;
+  }
+  p.cw_shift = chunked ? (p.cw == 64 ? 6 : (p.cw == 32 ? 5 : 4)) : -1;
+  p.stat_M = p.Ntile <= 64 ? 64 : 128;
+  p.st_rowbytes = p.cw * 2;
+  p.st_chunk_bytes = round_up(128 * p.st_rowbytes, 1024);
+  p.st_chunks = (p.Ntile + p.cw - 1) / p.cw;
+  if (p.mma_stats && p.st_chunks < p.stat_M / p.cw) p.st_chunks = p.stat_M / p.cw;   // the Gram A operand spans stat_M channels
+  p.st_buf_bytes = p.st_chunks * p.st_chunk_bytes;
+  p.acc_bufs = (p.mma_stats && 4 * p.Ntile > 512) ? 1 : 2;
+  const int wgt_total = used_taps * p.ncblk * p.b_sub_bytes;
+  p.w_resident = (g_opt_resident && p.n_ntiles == 1 && wgt_total <= 98304) ? 1 : 0;
   const int stats_bytes = round_up(2 * g.dC * 4, 16);
-  const int fixed = staging_bytes + stats_bytes + 8192 + 256 + 1024;
+  const int misc = 2048 /*ones*/ + stats_bytes + 16384 /*scratch*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+  p.st_bufs = g_opt_st_bufs == 1 ? 1 : 2;
+  auto fixed_bytes = [&]() { return p.st_bufs * p.st_buf_bytes + (p.w_resident ? wgt_total : 0) + misc; };
+  const int fixed = fixed_bytes();   // tile search budget (refined below)
 
   // tile / mode search
   double best = 1e30;
@@ -414,8 +612,8 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
         int rows_l = 128, nloads = taps, nsub = 1;
         if (mode == 1) { rows_l = (bh + g.kh - 1) * bw; nloads = g.kw; nsub = g.kh; if (bh + g.kh - 1 > 256) continue; }
         if (mode == 2) { rows_l = (bt + g.kt - 1) * bh * bw; nloads = 1; nsub = g.kt; if (bt + g.kt - 1 > 256) continue; }
-        const int stage = round_up(rows_l * rowbytes, 1024) + nsub * p.b_sub_bytes;
-        if (fixed + 2 * stage > TC_SMEM_MAX) continue;
+        const int stage = round_up(rows_l * rowbytes, 1024) + (p.w_resident ? 0 : nsub * p.b_sub_bytes);
+        if (fixed - p.st_buf_bytes + 2 * stage > TC_SMEM_MAX) continue;
         const double ntiles = (double)((g.dW + bw - 1) / bw) * ((g.dH + bh - 1) / bh) * ((g.dT + bt - 1) / bt);
         const double cost = ntiles * ((double)nloads * p.ncblk * (rows_l * rowbytes + nsub * p.b_box_bytes) +
                                       0.15 * taps * 128.0 * g.sC * 2.0) - 1e-3 * bw;
@@ -470,21 +668,32 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
     out->a_box[1] = p.bw; out->a_box[2] = p.bh; out->a_box[3] = p.bt + g.kt - 1;
   }
   p.a_box_bytes = rows_l * rowbytes;
-  p.stage_bytes = round_up(p.a_box_bytes, 1024) + p.nsub * p.b_sub_bytes;
-  int stages = (TC_SMEM_MAX - fixed) / p.stage_bytes;
+  p.stage_bytes = round_up(p.a_box_bytes, 1024) + (p.w_resident ? 0 : p.nsub * p.b_sub_bytes);
+  int stages = (TC_SMEM_MAX - fixed_bytes()) / p.stage_bytes;
+  if (stages < 4 && p.st_bufs == 2) {   // prefer pipeline depth over a second staging buffer
+    p.st_bufs = 1;
+    stages = (TC_SMEM_MAX - fixed_bytes()) / p.stage_bytes;
+  }
+  if (stages < 3 && p.w_resident) {
+    p.w_resident = 0;
+    p.stage_bytes = round_up(p.a_box_bytes, 1024) + p.nsub * p.b_sub_bytes;
+    stages = (TC_SMEM_MAX - fixed_bytes()) / p.stage_bytes;
+  }
   if (stages > g_opt_max_stages) stages = g_opt_max_stages;
   if (stages > 8) stages = 8;
   if (stages < 2) return false;
   p.num_stages = stages;
-  p.off_staging = stages * p.stage_bytes;
-  p.off_stats = p.off_staging + staging_bytes;
+  p.off_wgt = stages * p.stage_bytes;
+  p.off_staging = p.off_wgt + (p.w_resident ? wgt_total : 0);
+  p.off_ones = p.off_staging + p.st_bufs * p.st_buf_bytes;
+  p.off_stats = p.off_ones + 2048;
   p.off_scratch = p.off_stats + stats_bytes;
-  p.off_bars = p.off_scratch + 8192;
+  p.off_bars = p.off_scratch + 16384;
   int cols = 32;
-  while (cols < 2 * p.Ntile) cols <<= 1;
+  const int need_cols = (p.acc_bufs + (p.mma_stats ? 2 : 0)) * p.Ntile;
+  while (cols < need_cols) cols <<= 1;
   if (cols > 512) return false;
   p.tmem_cols = cols;
-  p.has_stats = has_stats ? 1 : 0;
   out->p = p;
   out->smem = (size_t)p.off_bars + 256 + 1024;
   const int sms = num_sms();
@@ -513,7 +722,7 @@ static int encode_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, 
 
 // destination view: explicit element strides (strided-dgrad parity classes write every s-th pixel)
 static int encode_view_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, long long sw_, long long sh_,
-                           long long st_, long long sb_, const int* box) {
+                           long long st_, long long sb_, const int* box, int layout) {
   PFN_encodeTiled enc = get_encode();
   DP_REQUIRE(enc != nullptr, DP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
@@ -521,8 +730,11 @@ static int encode_view_map(CUtensorMap* m, const void* ptr, int C, int W, int H,
   cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
   for (int i = 0; i < 5; ++i) b[i] = (cuuint32_t)box[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, b, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   layout == 2 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : (layout == 4 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : (layout == 6 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE)),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DP_REQUIRE(r == CUDA_SUCCESS, DP_ERR_CUDA, "cuTensorMapEncodeTiled(destination view) failed: CUresult %d", (int)r);
   return DP_OK;
 }
@@ -559,14 +771,14 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   const int taps = g.Kt * g.Kh * g.Kw;
   rc = encode_wgt_map(&tmB, wgt, taps * g.sC, g.dC, p.CB, p.Ntile, sw);
   if (rc != DP_OK) return rc;
-  const int dbox[5] = {p.Ntile, p.bw, p.bh, p.bt, 1};
+  const int dbox[5] = {p.cw, p.bw, p.bh, p.bt, 1};
   p.a_sw = (long long)g.vs_w * g.dC;
   p.a_sh = (long long)g.vs_h * g.FW * g.dC;
   p.a_st = (long long)g.vs_t * g.FH * g.FW * g.dC;
   p.a_sb = (long long)g.FT * g.FH * g.FW * g.dC;
   p.a_off = (((long long)g.vo_t * g.FH + g.vo_h) * g.FW + g.vo_w) * g.dC;
   rc = encode_view_map(&tmD, (const __nv_bfloat16*)dst + p.a_off, g.dC, g.dW, g.dH, g.dT, g.B, p.a_sw, p.a_sh, p.a_st,
-                       p.a_sb, dbox);
+                       p.a_sb, dbox, p.st_layout);
   if (rc != DP_OK) return rc;
 
   static std::once_flag attr_once;
@@ -577,7 +789,7 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   DP_REQUIRE(attr_err == cudaSuccess, DP_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s",
              cudaGetErrorString(attr_err));
   tc_gather_gemm_kernel<<<plan.grid, TC_THREADS, plan.smem, s>>>(tmA, tmB, tmD, p, (const __nv_bfloat16*)addend, part,
-                                                               (g_dbg && g_dbg_slots >= (size_t)plan.grid * 8) ? g_dbg : nullptr);
+                                                               (g_dbg && g_dbg_slots >= (size_t)148 * 16) ? g_dbg : nullptr);
   if (getenv("DP_DEBUG_PLAN"))
     fprintf(stderr, "[tc_gather] dst %dx%dx%dx%d src C=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d CB=%d ncblk=%d Ntile=%d stages=%d stage_bytes=%d a_box=%d tiles=%d grid=%d\n",
             g.dT, g.dH, g.dW, g.dC, g.sC, g.kt * g.kh * g.kw, p.bw, p.bh, p.bt, p.nloads, p.nsub, p.CB, p.ncblk, p.Ntile, p.num_stages,
