@@ -173,6 +173,9 @@ def run_ours(args):
     from dp_b200.loss import FocalLoss
     from dp_b200.optim import FusedClipAdamW
 
+    if os.environ.get("DP_BENCH_FAULT"):      # debugging aid: dump every thread's Python stack after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["DP_BENCH_FAULT"]), exit=True)
     rank, local_rank, world = dpd.init_distributed()
     _lib.require_device()
     dev = torch.device("cuda", local_rank)
@@ -299,8 +302,9 @@ def run_ours(args):
         kern = {}
         if rank == 0:
             Fn.PROFILER = Fn.KernelProfiler()
-            for i in range(args.profile_steps):
-                step(x_dev[i % n_host], y_dev)
+        for i in range(args.profile_steps):       # every rank steps (the step holds collectives); rank 0 records
+            step(x_dev[i % n_host], y_dev)
+        if rank == 0:
             kern = Fn.PROFILER.summary()
             Fn.PROFILER = None
         barrier()
