@@ -40,6 +40,9 @@ struct WgParams {
   int nloads, nsub, tap_sub_stride, taps;
   int Kp, Cp;
   int swap;  // 0: M side = dy (rows of D are k), 1: M side = x (rows of D are c)
+  // tap stacking (swap == 1, halo loads, Cp <= 64): `stack` sub-taps of one load are stacked along M -- their x windows
+  // are the same smem box at row shifts, i.e. MN-major chunks at a constant LBO -- so one MMA covers several taps
+  int stack, gpl, cbS, M_last;
   int n_mt, n_tg, lpg, nsplit, tiles_per_split, num_items;
   int cbX, cbD, chunksX, chunksD;
   int x_chunk_bytes, d_chunk_bytes, x_slot_bytes, d_slot_bytes, x_slots, d_slots;
@@ -157,21 +160,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int v_rowbytes = p.swap ? p.d_rowbytes : p.x_rowbytes;
     const uint32_t u_hi = smem_desc_hi((uint32_t)(8 * u_rowbytes), (uint32_t)(p.swap ? p.x_layout : p.d_layout));
     const uint32_t v_hi = smem_desc_hi((uint32_t)(8 * v_rowbytes), (uint32_t)(p.swap ? p.d_layout : p.x_layout));
-    const uint32_t u_lbo = (uint32_t)(p.swap ? p.x_chunk_bytes : p.d_chunk_bytes);
+    const uint32_t u_lbo = (uint32_t)(p.stack > 1 ? p.x_shift_bytes : (p.swap ? p.x_chunk_bytes : p.d_chunk_bytes));
     const uint32_t v_lbo = (uint32_t)(p.swap ? p.d_chunk_bytes : p.x_chunk_bytes);
     const uint32_t u_step = (uint32_t)(16 * u_rowbytes) >> 4, v_step = (uint32_t)(16 * v_rowbytes) >> 4;
     const uint32_t x_shift16 = (uint32_t)p.x_shift_bytes >> 4;
     const uint32_t d_lo0 = smem_desc_lo(sbase, p.swap ? v_lbo : u_lbo);
     const uint32_t x_lo0 = smem_desc_lo(sbase + (uint32_t)p.off_x, p.swap ? u_lbo : v_lbo);
     const uint32_t d_slot16 = (uint32_t)p.d_slot_bytes >> 4, x_slot16 = (uint32_t)p.x_slot_bytes >> 4;
-    const int nsub = p.nsub;
+    const int ngrp = p.stack > 1 ? p.gpl : p.nsub;                          // MMA groups (accumulator blocks) per load
+    const uint32_t x_adv16 = (uint32_t)(p.stack > 1 ? p.stack : 1) * x_shift16;
     const uint32_t N = (uint32_t)p.N;
     const bool leader = elect_one();
     long long w_full = 0, w_te = 0;
     const long long t_start = dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const WgItem it = wg_decode(p, item);
-      const uint32_t idesc = make_idesc_bf16(it.Mi, p.N, 1, 1);
+      const uint32_t idesc = make_idesc_bf16(p.stack > 1 ? 128 : it.Mi, p.N, 1, 1);
+      const uint32_t idesc_last = p.stack > 1 ? make_idesc_bf16(p.M_last, p.N, 1, 1) : idesc;
       long long c0 = dbg ? clock64() : 0;
       mbar_wait(tempty, tph ^ 1u);
       if (dbg) w_te += clock64() - c0;
@@ -191,18 +196,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           tc_fence_after();
           if (leader) {
             uint32_t x_lo = x_lo0 + (uint32_t)xs * x_slot16;
-            for (int s = 0; s < nsub; ++s) {
+            for (int g = 0; g < ngrp; ++g) {
               const uint32_t u_lo = p.swap ? x_lo : d_lo, v_lo = p.swap ? d_lo : x_lo;
-              umma_bf16_lh(tmem_d, u_lo, u_hi, v_lo, v_hi, idesc, first);
+              const uint32_t id = (g == ngrp - 1) ? idesc_last : idesc;
+              umma_bf16_lh(tmem_d, u_lo, u_hi, v_lo, v_hi, id, first);
 #pragma unroll
               for (int ks = 1; ks < WG_P / 16; ++ks)
-                umma_bf16_lh(tmem_d, u_lo + ks * u_step, u_hi, v_lo + ks * v_step, v_hi, idesc, 1u);
-              x_lo += x_shift16;
+                umma_bf16_lh(tmem_d, u_lo + ks * u_step, u_hi, v_lo + ks * v_step, v_hi, id, 1u);
+              x_lo += x_adv16;
               tmem_d += N;
             }
             umma_commit(x_empty(xs));
           } else {
-            tmem_d += N * (uint32_t)nsub;
+            tmem_d += N * (uint32_t)ngrp;
           }
           __syncwarp();
           if (++xs == XS) { xs = 0; xph ^= 1u; }
@@ -235,6 +241,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (dbg) w_tf += clock64() - c0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      if (p.stack > 1) {
+        for (int l = it.l0; l < it.l1; ++l) {
+          for (int g = 0; g < p.gpl; ++g) {
+            const int Mg = (g == p.gpl - 1) ? p.M_last : 128;
+            const int r = Mg == 128 ? (q * 32 + lane) : (q * 16 + lane);       // D row held by this thread
+            const int sub = r / p.cbS, c = r - sub * p.cbS;
+            const int sidx = g * p.stack + sub;
+            const bool ok = (Mg == 128 || lane < 16) && sidx < p.nsub && c < p.Cp;
+            const int tap = p.tap0[l] + sidx * p.tap_sub_stride;
+            const uint32_t col = (uint32_t)(((l - it.l0) * p.gpl + g) * p.N);
+            for (int n0 = 0; n0 < p.N; n0 += 16) {
+              uint32_t v[16];
+              tmem_ld16(taddr + col + (uint32_t)n0, v);
+              if (ok) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  base[((int64_t)(n0 + j) * p.taps + tap) * p.Cp + c] = __uint_as_float(v[j]);
+              }
+            }
+          }
+        }
+      } else
       for (int l = it.l0; l < it.l1; ++l) {
         for (int s = 0; s < p.nsub; ++s) {
           const int tap = p.tap0[l] + s * p.tap_sub_stride;
@@ -293,11 +321,12 @@ static PFN_encodeTiled wg_get_encode() {
   return fn;
 }
 
-static int g_wg_enable = 1, g_wg_halo = 1;
+static int g_wg_enable = 1, g_wg_halo = 1, g_wg_stack = 1;
 int wg_option(const char* name, int value, bool set) {
   int* slot = nullptr;
   if (!strcmp(name, "wg_enable")) slot = &g_wg_enable;
   else if (!strcmp(name, "wg_halo")) slot = &g_wg_halo;
+  else if (!strcmp(name, "wg_stack")) slot = &g_wg_stack;
   if (slot == nullptr) return -1;
   if (set) *slot = value;
   return *slot;
@@ -396,6 +425,16 @@ static bool plan_wgrad(const dp_conv_desc* d, WgPlan* out) {
   out->d_box[1] = p.bw; out->d_box[2] = p.bh; out->d_box[3] = p.bt; out->d_box[4] = 1;
 
   // ---- roles ----
+  p.stack = 1; p.gpl = p.nsub; p.cbS = 0; p.M_last = 0;
+  if (g_wg_stack && p.nsub > 1 && d->Cp <= 64 && d->Kp <= 256) {
+    const int cbS = d->Cp <= 32 ? 32 : 64, sf = 128 / cbS;
+    const int gpl = (p.nsub + sf - 1) / sf;
+    if (gpl * d->Kp <= 512) {
+      p.stack = sf; p.gpl = gpl; p.cbS = cbS;
+      const int cnt_last = p.nsub - (gpl - 1) * sf;
+      p.M_last = cnt_last * cbS <= 64 ? 64 : 128;
+    }
+  }
   int best_swap = -1;
   long best_key = 0;
   for (int swap = 0; swap < 2; ++swap) {
@@ -408,19 +447,19 @@ static bool plan_wgrad(const dp_conv_desc* d, WgPlan* out) {
     if (best_swap < 0 || key < best_key) { best_swap = swap; best_key = key; }
   }
   if (best_swap < 0) return false;
-  p.swap = best_swap;
+  p.swap = p.stack > 1 ? 1 : best_swap;
   const int CU = p.swap ? d->Cp : d->Kp, CV = p.swap ? d->Kp : d->Cp;
   p.N = CV;
-  p.lpg = 512 / (p.nsub * CV);
+  p.lpg = 512 / ((p.stack > 1 ? p.gpl : p.nsub) * CV);
   if (p.lpg > p.nloads) p.lpg = p.nloads;
   p.n_mt = (CU + 127) / 128;
   p.n_tg = (p.nloads + p.lpg - 1) / p.lpg;
   int cols = 32;
-  while (cols < p.lpg * p.nsub * p.N) cols <<= 1;
+  while (cols < p.lpg * (p.stack > 1 ? p.gpl : p.nsub) * p.N) cols <<= 1;
   p.tmem_cols = cols;
 
   // ---- chunking of the two operands ----
-  p.cbX = p.swap ? 64 : chunk_width(d->Cp);
+  p.cbX = p.stack > 1 ? p.cbS : (p.swap ? 64 : chunk_width(d->Cp));
   p.cbD = p.swap ? chunk_width(d->Kp) : 64;
   p.chunksX = p.swap ? (CU > 64 ? 2 : 1) : (d->Cp + p.cbX - 1) / p.cbX;
   p.chunksD = p.swap ? (d->Kp + p.cbD - 1) / p.cbD : (CU > 64 ? 2 : 1);
@@ -436,7 +475,8 @@ static bool plan_wgrad(const dp_conv_desc* d, WgPlan* out) {
   out->x_box[0] = p.cbX; out->d_box[0] = p.cbD;
 
   const int bar_bytes = 1024;
-  const int avail = WG_SMEM_MAX - 1024 - bar_bytes;
+  const int stack_pad = p.stack > 1 ? rup(p.stack * p.x_shift_bytes, 1024) : 0;
+  const int avail = WG_SMEM_MAX - 1024 - bar_bytes - stack_pad;
   p.d_slots = 3;
   if (p.d_slots * p.d_slot_bytes + 2 * p.x_slot_bytes > avail) p.d_slots = 2;
   int xs = (avail - p.d_slots * p.d_slot_bytes) / p.x_slot_bytes;
@@ -444,7 +484,8 @@ static bool plan_wgrad(const dp_conv_desc* d, WgPlan* out) {
   if (xs < 2) return false;
   p.x_slots = xs;
   p.off_x = p.d_slots * p.d_slot_bytes;
-  p.off_bars = p.off_x + p.x_slots * p.x_slot_bytes;
+  // stacked MMAs read up to `stack` shifted windows: the junk window of a partial stack may run past the last slot
+  p.off_bars = p.off_x + p.x_slots * p.x_slot_bytes + stack_pad;
   out->smem = (size_t)p.off_bars + bar_bytes + 1024;
   if (out->smem > (size_t)WG_SMEM_MAX) return false;
 

@@ -12,10 +12,6 @@ dev = "cuda"
 dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 LAYERS = [
     ("stem.temporal 45->32", 45, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), (21, 64, 64)),
-    ("conv2.temporal 72->32", 72, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), (21, 64, 64)),
-]
-_UNUSED = [
-    ("stem.temporal 45->32", 45, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), (21, 64, 64)),
     ("conv2.spatial 32->72", 32, 72, (1, 3, 3), (1, 1, 1), (0, 1, 1), (21, 64, 64)),
     ("conv2.temporal 72->32", 72, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), (21, 64, 64)),
     ("conv3.spatial 64->144", 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), (11, 32, 32)),
@@ -32,7 +28,7 @@ def run(name, fn):
     d = dbg[:148 * 8].view(148, 8).double()
     act = d[:, 1] > 0
     m = d[act].mean(0)
-    print(f"  {name:6s} {e0.elapsed_time(e1)*1e3:8.1f} us | producer: wait_empty {m[0]:9.0f} / total {m[1]:9.0f} | mma: wait_full {m[2]:9.0f} wait_tmem {m[3]:9.0f} / total {m[4]:9.0f} | epilogue: wait_tfull {m[5]:9.0f} / total {m[6]:9.0f}  (cycles, mean over {int(act.sum())} CTAs) | epi parts: waitfree+bar {d2[0]:.0f} drain {d2[1]:.0f} fence+bar {d2[2]:.0f} store {d2[3]:.0f}", flush=True)
+    print(f"  {name:6s} {e0.elapsed_time(e1)*1e3:7.1f}us |prod wait {m[0]/1e3:5.0f}k/{m[1]/1e3:5.0f}k |mma wfull {m[2]/1e3:5.0f}k wtmem {m[3]/1e3:5.0f}k /{m[4]/1e3:5.0f}k |epi wtfull {m[5]/1e3:5.0f}k /{m[6]/1e3:5.0f}k ({int(act.sum())} CTAs) | epi parts: waitfree+bar {d2[0]:.0f} drain {d2[1]:.0f} fence+bar {d2[2]:.0f} store {d2[3]:.0f}", flush=True)
 for (name, cin, cout, k, s, p, inp) in LAYERS:
     print(name, flush=True)
     x = torch.randn(B, *inp, Fn.ceil16(cin), device=dev).bfloat16(); x[..., cin:] = 0

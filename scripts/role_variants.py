@@ -6,10 +6,10 @@ from dp_b200 import _lib as L, functional as Fn
 B = 64
 lib = L.load(); L.require_device()
 dev = "cuda"
-dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
 LAYERS = [
-    ("stem.temporal 45->32", 45, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), (21, 64, 64)),
+    ("conv2.spatial 32->72", 32, 72, (1, 3, 3), (1, 1, 1), (0, 1, 1), (21, 64, 64)),
     ("conv2.temporal 72->32", 72, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), (21, 64, 64)),
+    ("conv3.temporal 144->64", 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), (11, 32, 32)),
 ]
 def run(name, fn):
     fn(); torch.cuda.synchronize()
@@ -29,8 +29,8 @@ for (name, cin, cout, k, s, p, inp) in LAYERS:
     st = L.stream_ptr()
     dy = torch.randn(gm.out_shape, device=dev).bfloat16(); dy[..., cout:] = 0
     dx = torch.empty_like(x)
-    for opts in ({}, {"tc_resident": 0}, {"tc_chunked": 0}, {"tc_st_bufs": 1}, {"tc_chunked": 0, "tc_st_bufs": 1}, {"tc_chunked": 0, "tc_st_bufs": 1, "tc_resident": 0}, {"tc_mma_stats": 0}):
+    for opts in ({}, {"tc_cb": 32}, {"tc_cb": 16}):
         for kk, v in opts.items(): L.set_option(kk, v)
         run("fwd   " + str(opts), lambda: L.check(lib.dp_conv_fwd(C.byref(d), x.data_ptr(), wf.data_ptr(), y.data_ptr(), part.data_ptr(), C.byref(nparts), 0, st)))
         run("dgrad " + str(opts), lambda: L.check(lib.dp_conv_dgrad(C.byref(d), dy.data_ptr(), wd.data_ptr(), None, dx.data_ptr(), 0, st)))
-        for kk in opts: L.set_option(kk, {"tc_st_bufs": 2}.get(kk, 1))
+        for kk in opts: L.set_option(kk, 0)
