@@ -68,7 +68,7 @@ SIGNATURES = {
     "dp_bn_eval_coeffs": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp]),
     "dp_bn_act_apply": (_i, [_vp, _vp, _vp, _f, _vp, _f, _vp, _i64, _i, _i, _vp]),
     "dp_bn_act_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _pint, _i64, _i, _i, _vp]),
-    "dp_bn_bwd_finalize": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp]),
+    "dp_bn_bwd_finalize": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dp_bn_act_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _i64, _i, _i, _vp]),
     "dp_add": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "dp_avgpool_fwd": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _vp]),

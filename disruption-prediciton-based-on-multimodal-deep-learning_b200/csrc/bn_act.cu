@@ -33,11 +33,13 @@ col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part) {  // f 
     const int cv = tid % vpr, rl = tid / vpr;
     f.init(cv * 8);                       // this thread's 8 channels never change: parameters live in registers
     int64_t r = r0 + rl;
-    for (; r + rpi < r1; r += 2 * rpi) {  // two independent rows in flight
+    for (; r + 3 * rpi < r1; r += 4 * rpi) {  // four independent rows in flight
       f(r * Cp + cv * 8, a, b);
       f((r + rpi) * Cp + cv * 8, a, b);
+      f((r + 2 * rpi) * Cp + cv * 8, a, b);
+      f((r + 3 * rpi) * Cp + cv * 8, a, b);
     }
-    if (r < r1) f(r * Cp + cv * 8, a, b);
+    for (; r < r1; r += rpi) f(r * Cp + cv * 8, a, b);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[0][tid * 8 + j] = a[j]; red[1][tid * 8 + j] = b[j]; }
@@ -74,12 +76,12 @@ struct BwdReduceF {
   const T* dz; const T* y; const T* out;
   const float* scale; const float* shift; const float* mean; const float* rstd;
   float slope, slope_res;
-  float r_scale[8], r_shift[8], r_mean[8], r_rstd[8];
+  float r_scale[8], r_shift[8];
+  // accumulates sum(g) and sum(g*y) with the RAW conv output y; bn_bwd_finalize turns the second into
+  // sum(g*xhat) = (sum(g*y) - mean*sum(g)) * rstd in fp64, so the streaming loop needs two parameters per channel
   __device__ __forceinline__ void init(int c0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      r_scale[j] = scale[c0 + j]; r_shift[j] = shift[c0 + j]; r_mean[j] = mean[c0 + j]; r_rstd[j] = rstd[c0 + j];
-    }
+    for (int j = 0; j < 8; ++j) { r_scale[j] = scale[c0 + j]; r_shift[j] = shift[c0 + j]; }
   }
   __device__ __forceinline__ void operator()(int64_t off, float* a, float* b) const {
     const f8 g = ld8(dz + off), v = ld8(y + off);
@@ -91,9 +93,8 @@ struct BwdReduceF {
       if (out != nullptr) gg *= (o.v[j] > 0.f ? 1.f : slope_res);
       const float u = fmaf(v.v[j], r_scale[j], r_shift[j]);
       gg *= (u > 0.f ? 1.f : slope);
-      const float xh = (v.v[j] - r_mean[j]) * r_rstd[j];
       a[j] += gg;
-      b[j] = fmaf(gg, xh, b[j]);
+      b[j] = fmaf(gg, v.v[j], b[j]);
     }
   }
 };
@@ -177,6 +178,7 @@ __global__ void bn_eval_coeffs_kernel(const float* rm, const float* rv, const fl
 
 __global__ void __launch_bounds__(FIN_CH * FIN_PL)
 bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, int Cp, double count,
+                       const float* __restrict__ mean, const float* __restrict__ rstd,
                        float* dgamma, float* dbeta, float* coef) {
   __shared__ double red[2][FIN_PL][FIN_CH];
   const int c = blockIdx.x * FIN_CH + threadIdx.x % FIN_CH, pl = threadIdx.x / FIN_CH;
@@ -184,6 +186,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, int Cp
   fin_reduce(part, nparts, Cp, c, pl, c < C, S, Q, red);
   if (pl != 0 || c >= Cp) return;
   if (c >= C) { coef[c] = 0.f; coef[Cp + c] = 0.f; return; }
+  Q = (Q - (double)mean[c] * S) * (double)rstd[c];   // sum(g*y) -> sum(g*xhat)
   if (dbeta != nullptr) dbeta[c] = (float)S;
   if (dgamma != nullptr) dgamma[c] = (float)Q;
   coef[c] = (float)(S / count);
@@ -207,10 +210,8 @@ bn_act_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, co
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
-  for (int64_t v = v0; v < nvec; v += stride) {
-    f8 a = ld8(y + v * 8);
-    f8 r;
-    if (residual != nullptr) r = ld8(residual + v * 8);
+  auto one = [&](const f8& a_in, const f8& r, int64_t v) {
+    f8 a = a_in;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float u = lrelu(fmaf(a.v[j], sc[j], sh[j]), slope);
@@ -218,6 +219,20 @@ bn_act_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, co
       a.v[j] = u;
     }
     st8(z + v * 8, a);
+  };
+  int64_t v = v0;
+  for (; v + stride < nvec; v += 2 * stride) {   // two independent vectors in flight per thread
+    const f8 a0 = ld8(y + v * 8), a1 = ld8(y + (v + stride) * 8);
+    f8 r0, r1;
+    if (residual != nullptr) { r0 = ld8(residual + v * 8); r1 = ld8(residual + (v + stride) * 8); }
+    one(a0, r0, v);
+    one(a1, r1, v + stride);
+  }
+  if (v < nvec) {
+    const f8 a0 = ld8(y + v * 8);
+    f8 r0;
+    if (residual != nullptr) r0 = ld8(residual + v * 8);
+    one(a0, r0, v);
   }
 }
 
@@ -357,13 +372,13 @@ DP_API int dp_bn_act_bwd_reduce(const void* dz, const void* y, const void* out, 
   return check_launch("dp_bn_act_bwd_reduce");
 }
 
-DP_API int dp_bn_bwd_finalize(const float* part, int nparts, int C, int Cp, double count, float* dgamma,
-                              float* dbeta, float* coef, void* stream) {
-  DP_REQUIRE(part && coef, DP_ERR_SHAPE, "dp_bn_bwd_finalize: NULL pointer");
+DP_API int dp_bn_bwd_finalize(const float* part, int nparts, int C, int Cp, double count, const float* mean,
+                              const float* rstd, float* dgamma, float* dbeta, float* coef, void* stream) {
+  DP_REQUIRE(part && coef && mean && rstd, DP_ERR_SHAPE, "dp_bn_bwd_finalize: NULL pointer");
   DP_REQUIRE(nparts > 0 && nparts <= DP_MAX_PARTS && C > 0 && Cp >= C && count > 0, DP_ERR_SHAPE,
              "dp_bn_bwd_finalize: bad sizes");
-  bn_bwd_finalize_kernel<<<ceil_div(Cp, FIN_CH), FIN_CH * FIN_PL, 0, as_stream(stream)>>>(part, nparts, C, Cp, count, dgamma, dbeta,
-                                                                          coef);
+  bn_bwd_finalize_kernel<<<ceil_div(Cp, FIN_CH), FIN_CH * FIN_PL, 0, as_stream(stream)>>>(part, nparts, C, Cp, count, mean, rstd,
+                                                                                        dgamma, dbeta, coef);
   return check_launch("dp_bn_bwd_finalize");
 }
 

@@ -401,8 +401,8 @@ def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope
     dgamma = torch.empty(d.K, dtype=torch.float32, device=dev)
     dbeta = torch.empty(d.K, dtype=torch.float32, device=dev)
     coef = torch.empty((2, d.Kp), dtype=torch.float32, device=dev)
-    L.check(lib.dp_bn_bwd_finalize(part.data_ptr(), nparts.value, d.K, d.Kp, float(geom.rows_out), dgamma.data_ptr(),
-                                   dbeta.data_ptr(), coef.data_ptr(), st), "dp_bn_bwd_finalize")
+    L.check(lib.dp_bn_bwd_finalize(part.data_ptr(), nparts.value, d.K, d.Kp, float(geom.rows_out), mean, rstd,
+                                   dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), st), "dp_bn_bwd_finalize")
     if not training:
         coef.zero_()  # eval-mode BN: statistics are constants, no mean/variance terms
     dy = torch.empty_like(y)

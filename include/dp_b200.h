@@ -135,13 +135,14 @@ int dp_bn_eval_coeffs(const float* running_mean, const float* running_var, const
 int dp_bn_act_apply(const void* y, const float* scale, const float* shift, float slope,
                     const void* residual, float slope_res, void* z, int64_t rows, int Cp,
                     int dtype, void* stream);
-/* backward of the above, pass 1: per-channel sum(g), sum(g*xhat) partials. */
+/* backward of the above, pass 1: per-channel sum(g), sum(g*y) partials (y = raw conv output). */
 int dp_bn_act_bwd_reduce(const void* dz, const void* y, const void* out,
                          const float* scale, const float* shift, const float* mean,
                          const float* rstd, float slope, float slope_res,
                          float* part, int* nparts, int64_t rows, int Cp, int dtype, void* stream);
-int dp_bn_bwd_finalize(const float* part, int nparts, int C, int Cp, double count,
-                       float* dgamma, float* dbeta, float* coef, void* stream);
+/* dbeta = sum(g), dgamma = sum(g*xhat) = (sum(g*y) - mean*sum(g))*rstd (fp64), coef = {dbeta, dgamma}/count */
+int dp_bn_bwd_finalize(const float* part, int nparts, int C, int Cp, double count, const float* mean,
+                       const float* rstd, float* dgamma, float* dbeta, float* coef, void* stream);
 /* pass 2: dy = scale*(g - coef0 - xhat*coef1); optionally dres = dz*lrelu'(out). */
 int dp_bn_act_bwd_apply(const void* dz, const void* y, const void* out,
                         const float* scale, const float* shift, const float* mean,

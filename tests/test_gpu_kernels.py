@@ -335,8 +335,8 @@ def test_bn_act_fwd_bwd(dtype, C_):
                                          Cp, Fn._code(yi), st_))
         dgamma, dbeta = torch.empty(C_, device=DEV), torch.empty(C_, device=DEV)
         coef = torch.empty((2, Cp), device=DEV)
-        L.check(lib.dp_bn_bwd_finalize(part.data_ptr(), nparts.value, C_, Cp, float(rows), dgamma.data_ptr(),
-                                       dbeta.data_ptr(), coef.data_ptr(), st_))
+        L.check(lib.dp_bn_bwd_finalize(part.data_ptr(), nparts.value, C_, Cp, float(rows), stats[0].data_ptr(),
+                                       stats[1].data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), st_))
         dyi = torch.empty_like(yi)
         dres = torch.empty_like(yi) if use_res else None
         L.check(lib.dp_bn_act_bwd_apply(dzi.data_ptr(), yi.data_ptr(), zi.data_ptr() if use_res else None,
