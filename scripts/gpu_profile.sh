@@ -8,9 +8,9 @@ CMD="python bench.py --steps 2 --warmup 3 --no-e2e --profile-steps 0 --no-cpu-ba
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1600 -c 700 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1
 echo "ncu launches rc=$?" >> gpurun_out/rc.txt
-ncu --set full --clock-control none --import-source on -k regex:tc_gather_gemm -s 70 -c 6 -o gpurun_out/prof_gather $CMD > gpurun_out/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tc_gather_gemm -s 66 -c 8 -o gpurun_out/prof_gather $CMD > gpurun_out/ncu2.log 2>&1
 echo "ncu gather rc=$?" >> gpurun_out/rc.txt
-ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 34 -c 6 -o gpurun_out/prof_wgrad $CMD > gpurun_out/ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 32 -c 8 -o gpurun_out/prof_wgrad $CMD > gpurun_out/ncu3.log 2>&1
 echo "ncu wgrad rc=$?" >> gpurun_out/rc.txt
 ncu --set full --clock-control none --import-source on -k regex:bn_act -s 100 -c 6 -o gpurun_out/prof_bn $CMD > gpurun_out/ncu4.log 2>&1
 echo "ncu bn rc=$?" >> gpurun_out/rc.txt

@@ -226,8 +226,14 @@ def test_full_size_bf16_mode_vs_oracle(loss_name, alpha, impl, clips):
         assert a <= 1.25 * b + 1e-2
     sd = model.state_dict()
     for k in sd:
-        if k.endswith("running_var") or k.endswith("running_mean"):
+        if k.endswith("running_var"):
             assert rel_max(sd[k], emu_state[k]) < 5e-3, k
+        if k.endswith("running_mean"):
+            # a channel mean is judged on the scale of that channel's standard deviation (several layers have
+            # means ~1e-4 sigma, where "relative to the mean" is meaningless); momentum 0.1 scales both sides
+            sigma = emu_state[k.replace("running_mean", "running_var")].sqrt()
+            err = ((sd[k].cpu() - emu_state[k]).abs() / sigma).max().item()
+            assert err < 1e-3, (k, err)
 
 
 def test_thresholded_label_agreement():
