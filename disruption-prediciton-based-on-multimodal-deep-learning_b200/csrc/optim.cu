@@ -11,12 +11,14 @@ constexpr int OPT_MAX_GRID = 1184;
 
 struct OptWs {
   unsigned int counter;
-  unsigned int pad[3];
+  unsigned int step;      // device-side step count (used when the host passes step == 0: CUDA-graph replay)
+  unsigned int pad[2];
   float partial[OPT_MAX_GRID];
 };
 
 __global__ void __launch_bounds__(OPT_THREADS)
-sqnorm_kernel(const float* __restrict__ g, int64_t n, float grad_scale, float* __restrict__ norm_out, OptWs* ws) {
+sqnorm_kernel(const float* __restrict__ g, int64_t n, float grad_scale, float* __restrict__ norm_out, OptWs* ws,
+              int dev_step) {
   float acc = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n >> 2;
@@ -46,13 +48,19 @@ sqnorm_kernel(const float* __restrict__ g, int64_t n, float grad_scale, float* _
     for (unsigned int k = 0; k < gridDim.x; ++k) t += (double)*reinterpret_cast<volatile float*>(&ws->partial[k]);
     norm_out[0] = (float)(sqrt(t) * (double)grad_scale);
     ws->counter = 0u;
+    if (dev_step) ws->step += 1u;
   }
 }
 
 __global__ void __launch_bounds__(OPT_THREADS)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
-             float max_norm, float grad_scale, const float* __restrict__ norm) {
+             float max_norm, float grad_scale, const float* __restrict__ norm, const OptWs* __restrict__ ws, int dev_step) {
+  if (dev_step) {   // bias corrections from the device-side step count
+    const float st = (float)ws->step;
+    bc1 = 1.f - powf(beta1, st);
+    bc2_sqrt = sqrtf(1.f - powf(beta2, st));
+  }
   float gs = grad_scale;
   if (max_norm > 0.f) {
     const float coef = max_norm / (norm[0] + 1e-6f);
@@ -85,20 +93,21 @@ DP_API int dp_clip_adamw_step(float* p, const float* g, float* m, float* v, int6
                               float beta2, float eps, float weight_decay, int step, float max_norm, float grad_scale,
                               float* norm_out, void* workspace, void* stream) {
   DP_REQUIRE(p && g && m && v && norm_out && workspace, DP_ERR_SHAPE, "dp_clip_adamw_step: NULL pointer");
-  DP_REQUIRE(n > 0 && step >= 1, DP_ERR_SHAPE, "dp_clip_adamw_step: n=%lld step=%d", (long long)n, step);
+  DP_REQUIRE(n > 0 && step >= 0, DP_ERR_SHAPE, "dp_clip_adamw_step: n=%lld step=%d", (long long)n, step);
+  const int dev_step = step == 0 ? 1 : 0;   // step == 0: count steps on the device (CUDA-graph capturable)
   DP_REQUIRE(((uintptr_t)g & 15) == 0, DP_ERR_ALIGN, "dp_clip_adamw_step: grad bucket must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   int64_t grid = (n / 4 + OPT_THREADS - 1) / OPT_THREADS;
   if (grid > OPT_MAX_GRID) grid = OPT_MAX_GRID;
   if (grid < 1) grid = 1;
-  sqnorm_kernel<<<(int)grid, OPT_THREADS, 0, st>>>(g, n, grad_scale, norm_out, (OptWs*)workspace);
+  sqnorm_kernel<<<(int)grid, OPT_THREADS, 0, st>>>(g, n, grad_scale, norm_out, (OptWs*)workspace, dev_step);
   int rc = check_launch("dp_clip_adamw_step/sqnorm");
   if (rc != DP_OK) return rc;
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2 = 1.f - powf(beta2, (float)step);
+  const float bc1 = 1.f - powf(beta1, (float)(step > 0 ? step : 1));
+  const float bc2 = 1.f - powf(beta2, (float)(step > 0 ? step : 1));
   int64_t g2 = (n + OPT_THREADS - 1) / OPT_THREADS;
   if (g2 > OPT_MAX_GRID) g2 = OPT_MAX_GRID;
   adamw_kernel<<<(int)g2, OPT_THREADS, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2),
-                                                max_norm, grad_scale, norm_out);
+                                                max_norm, grad_scale, norm_out, (const OptWs*)workspace, dev_step);
   return check_launch("dp_clip_adamw_step/adamw");
 }

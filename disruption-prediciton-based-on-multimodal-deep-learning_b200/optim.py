@@ -19,9 +19,10 @@ from . import functional as Fn
 
 class FusedClipAdamW(torch.optim.Optimizer):
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2, max_norm: Optional[float] = None):
+                 weight_decay: float = 1e-2, max_norm: Optional[float] = None, capturable: bool = False):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=max_norm)
         super().__init__(params, defaults)
+        self.capturable = capturable   # step count kept on the device: the step can live inside a CUDA graph
         self._flat = {}
         self.grad_scale = 1.0          # set to 1/world_size by the DP trainer (DDP-mean semantics)
         self.last_grad_norm = None     # device scalar tensor, no sync
@@ -89,7 +90,7 @@ class FusedClipAdamW(torch.optim.Optimizer):
             mn = group["max_norm"]
             L.check(lib.dp_clip_adamw_step(st["flat"].data_ptr(), g.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(),
                                            st["n"], float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                                           float(group["weight_decay"]), int(st["step"]),
+                                           float(group["weight_decay"]), 0 if self.capturable else int(st["step"]),
                                            float(mn) if mn else 0.0, float(self.grad_scale), st["norm"].data_ptr(),
                                            st["ws"].data_ptr(), L.stream_ptr()), "dp_clip_adamw_step")
             self.last_grad_norm = st["norm"]

@@ -171,7 +171,9 @@ int dp_loss_bwd_scale(const float* dlogits, const float* grad_out, const float* 
 /* ---- fused optimiser tail (src/train.py:63-66: clip_grad_norm_ + AdamW.step) ---- */
 size_t dp_optim_workspace(int64_t n);
 /* flat fp32 param/grad/moment buffers of n elements; decoupled weight decay (AdamW).
- * max_norm <= 0 disables clipping.  grad_scale multiplies g first (1/world for DP mean). */
+ * max_norm <= 0 disables clipping.  grad_scale multiplies g first (1/world for DP mean).
+ * step >= 1: bias-correction step given by the host; step == 0: the step count lives in `workspace` on the device
+ * and is incremented by each call (nothing host-dependent is baked into a captured CUDA graph). */
 int dp_clip_adamw_step(float* p, const float* g, float* m, float* v, int64_t n,
                        float lr, float beta1, float beta2, float eps, float weight_decay,
                        int step, float max_norm, float grad_scale, float* norm_out,
