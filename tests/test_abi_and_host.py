@@ -159,3 +159,28 @@ def test_shards_and_windows():
     assert len(buckets) == 6
     assert sum(p.numel() for b in buckets for p in b) == 1_587_523
     assert buckets[0][0] is m.linear[0].weight               # head first: its gradient is ready first
+
+
+def test_multimodal_surface_cpu():
+    """Config-4 model constructs on CPU with the reference's fusion-head structure; the 0D branch is
+    plain PyTorch and runs on CPU, the video branch refuses to (no CPU fallback)."""
+    from dp_b200.MultiModal import GradientBlending, MultiModalR2Plus1D, MultiModalR2Plus1D_GB, Transformer
+    args_v = {"layer_sizes": [1, 1, 1, 1], "alpha": 0.01}
+    args_t = dict(n_features=18, kernel_size=5, feature_dims=128, max_len=21, n_layers=1, n_heads=8,
+                  dim_feedforward=256, dropout=0.0)
+    m = MultiModalR2Plus1D(2, args_v, args_t)
+    assert m.connector[0].in_features == 256 and m.classifier[-1].out_features == 2      # MultiModal.py:21-31
+    g = MultiModalR2Plus1D_GB(2, args_v, args_t)
+    assert g.use_stream == "multi-GB" and g.vis_model.linear[0].in_features == 128
+    t = Transformer(n_features=18, feature_dims=128, max_len=21, n_heads=8, dim_feedforward=256, dropout=0.0).eval()
+    out = t(torch.randn(3, 21, 18))
+    assert out.shape == (3, 2) and torch.isfinite(out).all()
+    assert t.encoder.src_mask.shape == (21, 21) and torch.isinf(t.encoder.src_mask[0, 1]) and t.encoder.src_mask[1, 0] == 0
+    gb = GradientBlending(torch.nn.CrossEntropyLoss(), torch.nn.CrossEntropyLoss(), torch.nn.CrossEntropyLoss(), 0.1, 0.4, 0.5)
+    lo = torch.randn(4, 2)
+    y = torch.tensor([0, 1, 1, 0])
+    ce = torch.nn.functional.cross_entropy(lo, y)
+    assert abs(gb(lo, lo, lo, y).item() - ce.item()) < 1e-6                               # weights sum to 1
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.DpError):
+            m(torch.zeros(2, 3, 9, 64, 64), torch.zeros(2, 21, 18))
