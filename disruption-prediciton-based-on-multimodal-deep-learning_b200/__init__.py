@@ -14,6 +14,7 @@ from . import distributed
 from . import inference
 from . import graph
 from . import MultiModal
+from . import slowfast
 from .functional import compute_mode, get_compute_mode, set_compute_mode, set_conv_impl
 from .loss import CELoss, FocalLoss, ImbalancedDatasetSampler, LDAMLoss, drw_betas, drw_class_weights, rw_class_weights
 from .R2Plus1D import (Conv3dBlock, R2Plus1DClassifier, R2Plus1DNet, SpatioTemporalConv, SpatioTemporalResBlock,

@@ -475,6 +475,72 @@ class ConvBnActFn(torch.autograd.Function):
         return dx, dw, dg, db, None
 
 
+class ConvBnActResFn(torch.autograd.Function):
+    """Conv3d -> BatchNorm3d -> LeakyReLU(slope) -> (+ residual) -> LeakyReLU(slope_res) as ONE layer with the
+    residual add fused into the BN-apply pass (the tail of a ResNet bottleneck, reference resnet.py:193-200, uses
+    slope 1 = no activation before the add and slope_res 0 = ReLU after it).
+    inputs: x, weight, gamma, beta, residual, mod, slope_res."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, residual, mod, slope_res):
+        training = mod.training
+        rm, rv = (mod.bn.running_mean, mod.bn.running_var) if mod.bn.track_running_stats else (None, None)
+        if not training and rm is None:
+            training = True
+        z, saved = layer_forward(x, weight, gamma, beta, rm, rv, mod._cfg, training, residual=residual.contiguous(),
+                                 slope_res=slope_res, cache=mod._packed)
+        xs, y, out, stats, wd, geom = saved
+        ctx.save_for_backward(xs, y, out, stats, wd)
+        ctx.geom, ctx.cfg, ctx.training, ctx.wshape, ctx.slope_res = geom, mod._cfg, training, weight.shape, float(slope_res)
+        return z
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dz):
+        xs, y, out, stats, wd = ctx.saved_tensors
+        dx, dw, dg, db, dres = layer_backward((xs, y, out, stats, wd, ctx.geom), dz, ctx.wshape, ctx.cfg, ctx.training,
+                                              ctx.slope_res, ctx.needs_input_grad[0], want_dres=True)
+        return dx, dw, dg, db, dres, None, None
+
+
+class ConvFn(torch.autograd.Function):
+    """A bare Conv3d (bias-free) on internal tensors: the lateral connections of SlowFast
+    (reference slowfast.py:56-63) have neither normalisation nor activation.  inputs: x, weight, mod."""
+
+    @staticmethod
+    def forward(ctx, x, weight, mod):
+        lib = L.load()
+        cfg = mod._cfg
+        geom = conv_geom(cfg.C, cfg.K, cfg.kernel, cfg.stride, cfg.padding, x)
+        wf, wd = pack_weights(weight, geom, x.dtype, mod._packed)
+        y = torch.empty(geom.out_shape, dtype=x.dtype, device=x.device)
+        L.check(lib.dp_conv_fwd(C.byref(geom.desc), x.data_ptr(), wf.data_ptr(), y.data_ptr(), None, None, _STATE["impl"],
+                                L.stream_ptr()), "dp_conv_fwd")
+        ctx.save_for_backward(x, wd)
+        ctx.geom, ctx.wshape = geom, weight.shape
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, wd = ctx.saved_tensors
+        lib = L.load()
+        geom, d, st, impl = ctx.geom, ctx.geom.desc, L.stream_ptr(), _STATE["impl"]
+        dy = dy.contiguous()
+        dw = torch.empty(ctx.wshape, dtype=torch.float32, device=x.device)
+        if geom.ws_bytes is None:
+            geom.ws_bytes = int(lib.dp_conv_wgrad_workspace(C.byref(d), impl))
+        ws = _workspace(geom.ws_bytes, x.device)
+        L.check(lib.dp_conv_wgrad(C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(), impl,
+                                  st), "dp_conv_wgrad")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            L.check(lib.dp_conv_dgrad(C.byref(d), dy.data_ptr(), wd.data_ptr(), None, dx.data_ptr(), impl, st),
+                    "dp_conv_dgrad")
+        return dx, dw, None
+
+
 _STEM_GEOMS = {}
 
 

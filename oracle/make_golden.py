@@ -34,6 +34,46 @@ def import_reference():
     return R2Plus1DClassifier, FocalLoss, LDAMLoss, CELoss
 
 
+def slowfast_golden():
+    """E: SlowFast [1,2,2,1] (config 3): seed-42 state summary, the constructor probe's BatchNorm buffers (they are
+    rounding-noise driven in the deep layers, so they are stored, not re-derived) and one small training step."""
+    from src.models.slowfast import SlowFast
+    from src.models.resnet import Bottleneck3D
+    from src.loss import FocalLoss
+    out = {}
+    T, H, W, B = 20, 64, 64, 4
+    torch.manual_seed(42)
+    m = SlowFast((3, T, H, W), Bottleneck3D, [1, 2, 2, 1], 4, 1, 2, 1.0)
+    sd = m.state_dict()
+    out["keys"] = np.array(list(sd.keys()))
+    out["shapes"] = np.array([str(tuple(v.shape)) for v in sd.values()])
+    out["summary"] = np.stack([summarise(v) for v in sd.values()])
+    bn_keys = [k for k in sd if k.endswith("running_mean") or k.endswith("running_var")]
+    out["init_bn_keys"] = np.array(bn_keys)
+    out["init_bn_values"] = np.concatenate([sd[k].numpy().reshape(-1) for k in bn_keys]).astype(np.float32)
+    x, y = synthetic(B, T, H, W)
+    y[0], y[1] = 0, 1
+    out["y"] = y.numpy()
+    w = torch.FloatTensor([0.98, 0.02])
+    m.train()
+    logits = m(x)
+    loss = FocalLoss(weight=w, gamma=2.0)(logits, y)
+    loss.backward()
+    out["logits"] = logits.detach().numpy()
+    out["loss"] = np.array(loss.item())
+    names = [n for n, p in m.named_parameters()]
+    out["grad_names"] = np.array(names)
+    out["grad_norm"] = np.array([0.0 if p.grad is None else p.grad.double().norm().item() for _, p in m.named_parameters()])
+    out["grad_summary"] = np.stack([summarise(p.grad if p.grad is not None else torch.zeros(1)) for _, p in m.named_parameters()])
+    sd2 = m.state_dict()
+    out["bn_summary"] = np.stack([summarise(sd2[k]) for k in bn_keys])
+    m.eval()
+    with torch.no_grad():
+        out["eval_logits"] = m(x).numpy()
+    np.savez_compressed(os.path.join(OUT, "slowfast_step.npz"), **out)
+    print("slowfast: %d keys, loss %.6f" % (len(sd), loss.item()))
+
+
 def summarise(t: torch.Tensor) -> np.ndarray:
     """[sum, sum|.|, first 4 values] in float64 -- enough to pin a tensor without storing it."""
     f = t.detach().double().reshape(-1)
@@ -159,6 +199,7 @@ def main():
         w = (1.0 - beta) / np.array(eff)
         out[f"drw_small_e{epoch}"] = torch.FloatTensor(w / np.sum(w) * 2).numpy()
     np.savez_compressed(os.path.join(OUT, "class_weights.npz"), **out)
+    slowfast_golden()
     print("wrote", sorted(os.listdir(OUT)))
 
 

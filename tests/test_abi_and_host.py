@@ -184,3 +184,27 @@ def test_multimodal_surface_cpu():
     if not torch.cuda.is_available():
         with pytest.raises(_lib.DpError):
             m(torch.zeros(2, 3, 9, 64, 64), torch.zeros(2, 21, 18))
+
+
+def test_slowfast_surface_cpu(golden_dir):
+    """Config-3 model: seed-42 construction gives the reference's 339 state-dict keys, shapes and weights
+    (fixture from the unmodified reference); BatchNorm buffers carry the deterministic part of the reference's
+    constructor probe."""
+    from dp_b200.slowfast import Bottleneck3D, SlowFast
+    gold = np.load(os.path.join(golden_dir, "slowfast_step.npz"))
+    torch.manual_seed(42)
+    m = SlowFast((3, 20, 64, 64), Bottleneck3D, [1, 2, 2, 1], 4, 1, 2, 1.0)
+    sd = m.state_dict()
+    assert list(sd.keys()) == [str(k) for k in gold["keys"]] and len(sd) == 339
+    assert sum(p.numel() for p in m.parameters()) == 1_076_526                    # SURVEY 8a a13
+    for k, shape, ref in zip(gold["keys"], gold["shapes"], gold["summary"]):
+        t = sd[str(k)]
+        assert str(tuple(t.shape)) == str(shape), k
+        if "running_" in str(k) or "num_batches" in str(k):
+            continue
+        f = t.detach().double().reshape(-1)
+        assert abs(f.sum().item() - ref[0]) <= 1e-6 * max(1.0, ref[1]) and abs(f.abs().sum().item() - ref[1]) <= 1e-6 * max(1.0, ref[1]), k
+    assert int(sd["encoder.slownet.layer0.1.num_batches_tracked"]) == 1
+    assert torch.allclose(sd["encoder.fastnet.layer1.0.bn1.running_var"], torch.full((4,), 0.9))
+    assert torch.allclose(sd["encoder.slownet.layer0.1.running_mean"], 0.1 * sd["encoder.slownet.layer0.0.bias"])
+    assert m.classifier.classifier[0].in_features == 640
