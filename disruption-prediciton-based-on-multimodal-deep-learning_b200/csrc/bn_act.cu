@@ -17,6 +17,8 @@ constexpr int RED_THREADS = 256;
 template <typename F>
 __global__ void __launch_bounds__(RED_THREADS)
 col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part) {  // f by value: per-thread register copy
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[2][RED_THREADS * 8];
   const int vpr = Cp >> 3;                       // 8-channel vectors per row
   const int rpi = RED_THREADS / vpr;             // rows per iteration
@@ -105,10 +107,10 @@ int bn_stats_launch(const void* y, int64_t rows, int Cp, int dtype, float* part,
   const int grid = reduce_grid(rows);
   if (dtype == DP_BF16) {
     StatsF<__nv_bfloat16> f{(const __nv_bfloat16*)y};
-    col_reduce2_kernel<<<grid, RED_THREADS, 0, s>>>(f, rows, Cp, part);
+    launch_pdl(col_reduce2_kernel<StatsF<__nv_bfloat16>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part);
   } else {
     StatsF<float> f{(const float*)y};
-    col_reduce2_kernel<<<grid, RED_THREADS, 0, s>>>(f, rows, Cp, part);
+    launch_pdl(col_reduce2_kernel<StatsF<float>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part);
   }
   *nparts = grid;
   return check_launch("bn_stats");
@@ -144,6 +146,8 @@ bn_finalize_kernel(const float* __restrict__ part, int nparts, int C, int Cp, do
                    float momentum, float* running_mean, float* running_var,
                    float* mean, float* rstd, float* scale, float* shift) {
   __shared__ double red[2][FIN_PL][FIN_CH];
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * FIN_CH + threadIdx.x % FIN_CH, pl = threadIdx.x / FIN_CH;
   double S, Q;
   fin_reduce(part, nparts, Cp, c, pl, c < C, S, Q, red);
@@ -181,6 +185,8 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, int Cp
                        const float* __restrict__ mean, const float* __restrict__ rstd,
                        float* dgamma, float* dbeta, float* coef) {
   __shared__ double red[2][FIN_PL][FIN_CH];
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * FIN_CH + threadIdx.x % FIN_CH, pl = threadIdx.x / FIN_CH;
   double S, Q;
   fin_reduce(part, nparts, Cp, c, pl, c < C, S, Q, red);
@@ -201,6 +207,8 @@ __global__ void __launch_bounds__(256)
 bn_act_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                     float slope, const T* __restrict__ residual, float slope_res, T* __restrict__ z,
                     int64_t nvec, int Cp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vpr = Cp >> 3;
   const int64_t total = (int64_t)gridDim.x * blockDim.x;
   const int64_t stride = (total / vpr) * vpr;
@@ -243,6 +251,8 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y, const
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ coef, float slope, float slope_res,
                         T* __restrict__ dy, T* __restrict__ dres, int64_t nvec, int Cp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vpr = Cp >> 3;
   const int64_t total = (int64_t)gridDim.x * blockDim.x;
   const int64_t stride = (total / vpr) * vpr;
@@ -317,9 +327,8 @@ DP_API int dp_bn_finalize(const float* part, int nparts, int C, int Cp, double c
              "dp_bn_finalize: bad sizes (nparts=%d C=%d Cp=%d)", nparts, C, Cp);
   DP_REQUIRE((running_mean == nullptr) == (running_var == nullptr), DP_ERR_SHAPE,
              "dp_bn_finalize: running_mean/var must both be given or both NULL");
-  bn_finalize_kernel<<<ceil_div(Cp, FIN_CH), FIN_CH * FIN_PL, 0, as_stream(stream)>>>(part, nparts, C, Cp, count, gamma, beta, eps,
-                                                                      momentum, running_mean, running_var, mean, rstd,
-                                                                      scale, shift);
+  launch_pdl(bn_finalize_kernel, dim3(ceil_div(Cp, FIN_CH)), dim3(FIN_CH * FIN_PL), 0, as_stream(stream), part, nparts, C, Cp, count,
+             gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift);
   return check_launch("dp_bn_finalize");
 }
 
@@ -340,9 +349,9 @@ DP_API int dp_bn_act_apply(const void* y, const float* scale, const float* shift
   const int grid = ew_grid(nvec, Cp / 8);
   const size_t sm = 0;
   if (dtype == DP_BF16)
-    bn_act_apply_kernel<__nv_bfloat16><<<grid, 256, sm, as_stream(stream)>>>(
-        (const __nv_bfloat16*)y, scale, shift, slope, (const __nv_bfloat16*)residual, slope_res, (__nv_bfloat16*)z,
-        nvec, Cp);
+    launch_pdl(bn_act_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(256), sm, as_stream(stream),
+               (const __nv_bfloat16*)y, scale, shift, slope, (const __nv_bfloat16*)residual, slope_res, (__nv_bfloat16*)z,
+               nvec, Cp);
   else
     bn_act_apply_kernel<float><<<grid, 256, sm, as_stream(stream)>>>((const float*)y, scale, shift, slope,
                                                                      (const float*)residual, slope_res, (float*)z,
@@ -362,11 +371,11 @@ DP_API int dp_bn_act_bwd_reduce(const void* dz, const void* y, const void* out, 
   if (dtype == DP_BF16) {
     BwdReduceF<__nv_bfloat16> f{(const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, (const __nv_bfloat16*)out,
                                 scale, shift, mean, rstd, slope, slope_res};
-    col_reduce2_kernel<<<grid, RED_THREADS, 0, s>>>(f, rows, Cp, part);
+    launch_pdl(col_reduce2_kernel<BwdReduceF<__nv_bfloat16>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part);
   } else {
     BwdReduceF<float> f{(const float*)dz, (const float*)y, (const float*)out, scale, shift, mean, rstd, slope,
                         slope_res};
-    col_reduce2_kernel<<<grid, RED_THREADS, 0, s>>>(f, rows, Cp, part);
+    launch_pdl(col_reduce2_kernel<BwdReduceF<float>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part);
   }
   *nparts = grid;
   return check_launch("dp_bn_act_bwd_reduce");
@@ -377,8 +386,8 @@ DP_API int dp_bn_bwd_finalize(const float* part, int nparts, int C, int Cp, doub
   DP_REQUIRE(part && coef && mean && rstd, DP_ERR_SHAPE, "dp_bn_bwd_finalize: NULL pointer");
   DP_REQUIRE(nparts > 0 && nparts <= DP_MAX_PARTS && C > 0 && Cp >= C && count > 0, DP_ERR_SHAPE,
              "dp_bn_bwd_finalize: bad sizes");
-  bn_bwd_finalize_kernel<<<ceil_div(Cp, FIN_CH), FIN_CH * FIN_PL, 0, as_stream(stream)>>>(part, nparts, C, Cp, count, mean, rstd,
-                                                                                        dgamma, dbeta, coef);
+  launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(Cp, FIN_CH)), dim3(FIN_CH * FIN_PL), 0, as_stream(stream), part, nparts, C, Cp,
+             count, mean, rstd, dgamma, dbeta, coef);
   return check_launch("dp_bn_bwd_finalize");
 }
 
@@ -394,9 +403,9 @@ DP_API int dp_bn_act_bwd_apply(const void* dz, const void* y, const void* out, c
   const int grid = ew_grid(nvec, Cp / 8);
   const size_t sm = 0;
   if (dtype == DP_BF16)
-    bn_act_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, sm, as_stream(stream)>>>(
-        (const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, (const __nv_bfloat16*)out, scale, shift, mean, rstd, coef,
-        slope, slope_res, (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, nvec, Cp);
+    launch_pdl(bn_act_bwd_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(256), sm, as_stream(stream),
+               (const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, (const __nv_bfloat16*)out, scale, shift, mean, rstd, coef,
+               slope, slope_res, (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, nvec, Cp);
   else
     bn_act_bwd_apply_kernel<float><<<grid, 256, sm, as_stream(stream)>>>(
         (const float*)dz, (const float*)y, (const float*)out, scale, shift, mean, rstd, coef, slope, slope_res,

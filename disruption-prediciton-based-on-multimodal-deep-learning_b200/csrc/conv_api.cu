@@ -25,6 +25,8 @@ static int validate(const dp_conv_desc* d) {
 template <typename T>
 __global__ void pack_weights_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd,
                                     int K, int C, int Kp, int Cp, int taps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)Kp * taps * Cp;
   if (idx >= total) return;
@@ -59,8 +61,8 @@ DP_API int dp_pack_weights(const dp_conv_desc* d, const float* w, void* w_fwd, v
   const int64_t total = (int64_t)d->Kp * taps * d->Cp;
   const int grid = ceil_div(total, 256);
   if (d->dtype == DP_BF16)
-    pack_weights_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(
-        w, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad, d->K, d->C, d->Kp, d->Cp, taps);
+    launch_pdl(pack_weights_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), w, (__nv_bfloat16*)w_fwd,
+               (__nv_bfloat16*)w_dgrad, d->K, d->C, d->Kp, d->Cp, taps);
   else
     pack_weights_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(w, (float*)w_fwd, (float*)w_dgrad, d->K, d->C,
                                                                     d->Kp, d->Cp, taps);

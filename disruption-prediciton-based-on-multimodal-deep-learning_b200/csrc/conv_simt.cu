@@ -182,6 +182,8 @@ wgrad_kernel(Geom g, const T* __restrict__ x, const T* __restrict__ dy, float* _
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                     int nsplit, int K, int C, int Kp, int Cp, int taps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = K * taps * Cp;
   if (idx >= total) return;
@@ -204,7 +206,7 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
 int wgrad_reduce_launch(const float* partial, float* dw, int nsplit, int K, int C, int Kp, int Cp, int taps,
                         cudaStream_t s) {
   const int total = K * taps * Cp;
-  wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, s>>>(partial, dw, nsplit, K, C, Kp, Cp, taps);
+  launch_pdl(wgrad_reduce_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, s, partial, dw, nsplit, K, C, Kp, Cp, taps);
   return check_launch("conv_wgrad_reduce");
 }
 

@@ -126,9 +126,11 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       fence_proxy_async_smem();
     }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only below
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t col_g = (uint32_t)(p.acc_bufs * p.Ntile), col_s = col_g + (uint32_t)p.Ntile;
 
@@ -788,7 +790,7 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   });
   DP_REQUIRE(attr_err == cudaSuccess, DP_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s",
              cudaGetErrorString(attr_err));
-  tc_gather_gemm_kernel<<<plan.grid, TC_THREADS, plan.smem, s>>>(tmA, tmB, tmD, p, (const __nv_bfloat16*)addend, part,
+  launch_pdl(tc_gather_gemm_kernel, dim3(plan.grid), dim3(TC_THREADS), plan.smem, s, tmA, tmB, tmD, p, (const __nv_bfloat16*)addend, part,
                                                                (g_dbg && g_dbg_slots >= (size_t)148 * 16) ? g_dbg : nullptr);
   if (getenv("DP_DEBUG_PLAN"))
     fprintf(stderr, "[tc_gather] dst %dx%dx%dx%d src C=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d CB=%d ncblk=%d Ntile=%d stages=%d stage_bytes=%d a_box=%d tiles=%d grid=%d\n",
@@ -921,12 +923,14 @@ int tc_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const vo
 
 DP_API int dp_set_option(const char* name, int value) {
   if (name == nullptr) return DP_ERR_SHAPE;
+  if (!strcmp(name, "pdl")) { dp::g_pdl = value ? 1 : 0; return DP_OK; }
   if (dp::tc_option(name, value, true) >= 0 || dp::wg_option(name, value, true) >= 0) return DP_OK;
   dp::set_error("dp_set_option: unknown option '%s'", name);
   return DP_ERR_UNSUPPORTED;
 }
 DP_API int dp_get_option(const char* name) {
   if (name == nullptr) return -1;
+  if (!strcmp(name, "pdl")) return dp::g_pdl;
   const int v = dp::tc_option(name, 0, false);
   return v >= 0 ? v : dp::wg_option(name, 0, false);
 }

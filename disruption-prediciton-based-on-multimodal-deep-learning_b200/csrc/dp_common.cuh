@@ -38,6 +38,24 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 
 int num_sms();
 
+// ---- programmatic dependent launch (PDL) ----
+// A step is ~370 short kernels; launched with programmatic stream serialization a kernel's CTAs may become resident
+// while the previous kernel drains (its prologue overlaps the predecessor's tail).  Every kernel launched this way
+// executes pdl_wait() before its first global-memory access and pdl_launch_dependents() at its start.
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // optional device buffer for per-role cycle counters (dp_set_debug_buffer); nullptr in normal operation
 extern long long* g_dbg;
 extern size_t g_dbg_slots;

@@ -105,9 +105,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0 && lane == 0) {
@@ -564,7 +566,7 @@ int tc_conv_wgrad_view(const dp_conv_desc* d, const long long* xstrides, const v
   });
   DP_REQUIRE(attr_err == cudaSuccess, DP_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s",
              cudaGetErrorString(attr_err));
-  wgrad_tc_kernel<<<plan.grid, WG_THREADS, plan.smem, s>>>(tmX, tmD, p, (float*)ws,
+  launch_pdl(wgrad_tc_kernel, dim3(plan.grid), dim3(WG_THREADS), plan.smem, s, tmX, tmD, p, (float*)ws,
                                                            (g_dbg && g_dbg_slots >= (size_t)plan.grid * 8) ? g_dbg : nullptr);
   if (getenv("DP_DEBUG_PLAN"))
     fprintf(stderr, "[tc_wgrad] out %dx%dx%d Kp=%d Cp=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d swap=%d N=%d n_mt=%d n_tg=%d lpg=%d cbX=%d cbD=%d xslots=%d dslots=%d xslot=%d dslot=%d nsplit=%d tiles/split=%d grid=%d\n",

@@ -72,7 +72,8 @@ int         dp_device_check(void);
 int         dp_num_sms(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long dp_launch_count(void);
-/* tuning / debug switches: "tc_enable", "tc_halo", "tc_strided", "tc_max_stages", "wg_enable", "wg_halo" */
+/* tuning / debug switches: "tc_enable", "tc_halo", "tc_strided", "tc_max_stages", "tc_mma_stats", "tc_resident",
+ * "wg_enable", "wg_halo", "wg_stack", "pdl" (programmatic dependent launch of the hot kernels) */
 int         dp_set_option(const char* name, int value);
 int         dp_get_option(const char* name);
 /* development aid: device buffer (>= 8 int64 per CTA) receiving per-role wait/busy cycle counters of the tcgen05
