@@ -41,6 +41,34 @@ FWD_GFLOP_PER_CLIP = 22.748
 TRAIN_GFLOP_PER_CLIP = 67.11   # fwd + dgrad + wgrad without the stem's unused dgrad
 
 
+def measured_traffic(kernel_family: str):
+    """Average DRAM bytes per launch of the dominant kernel family from the committed `ncu --set full` capture
+    (profiles/*_prof_*_raw.csv, dram__bytes_read.sum + dram__bytes_write.sum); None if no capture is present."""
+    import csv
+    import glob
+    tag = {"tc_gather_gemm": "gather", "tc_wgrad": "wgrad"}.get(kernel_family, "bn")
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_prof_{tag}_raw.csv")))
+    if not files:
+        return None, None
+    rows = list(csv.reader(open(files[-1])))
+    if len(rows) < 3:
+        return None, None
+    h, units = rows[0], rows[1]
+    unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n = 0.0, 0
+    for r in rows[2:]:
+        try:
+            v = 0.0
+            for col in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = h.index(col)
+                v += float(r[i]) * unit_scale.get(units[i], 1.0)
+            tot += v
+            n += 1
+        except (ValueError, IndexError):
+            continue
+    return (tot / n if n else None), os.path.basename(files[-1])
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -250,10 +278,14 @@ def run_ours(args):
             loss = step(x_dev[i % n_host], y_dev)
         barrier()
         assert torch.isfinite(loss).item(), "non-finite loss in warm-up"
-        if args.graph and world == 1:
+        if args.graph:
             from dp_b200.graph import GraphedTrainStep
             loss = None      # drop the eager autograd graph (its AccumulateGrad nodes sit on the default stream)
-            graphed = GraphedTrainStep(model, loss_fn, opt, x_dev[0], y_dev, warmup=1)
+            if reducer is not None:    # data parallel: bucket zeroing and the all-reduce waits are part of the graph
+                graphed = GraphedTrainStep(model, loss_fn, opt, x_dev[0], y_dev, warmup=1,
+                                           pre_backward=reducer.zero_grad, post_backward=reducer.finish)
+            else:
+                graphed = GraphedTrainStep(model, loss_fn, opt, x_dev[0], y_dev, warmup=1)
             for i in range(max(3, args.warmup)):
                 loss = run_step(x_dev[i % n_host], y_dev)
             barrier()
@@ -329,7 +361,9 @@ def run_ours(args):
         barrier()
 
     if rank != 0:
-        return
+        # NCCL teardown blocks while a captured graph still holds collectives: leave without destructors
+        sys.stdout.flush()
+        os._exit(0)
     clips = B * world * args.steps
     value = clips / (ms_dev / 1e3)
     e2e_value = clips / (ms_e2e / 1e3) if not args.no_e2e else None
@@ -345,10 +379,12 @@ def run_ours(args):
         top = max(fam_rows, key=lambda k: fam_rows[k]["ms_per_step"])
         r = fam_rows[top]
         n_l = max(1, r["launches_per_step"])
+        traffic, traffic_src = measured_traffic(top)
         if kern[top]["flops"] > 0:
             peak = peaks["bf16_tflops_sustained"]
             roofline = {"kernel": top, "bound": "tensor", "achieved": r["tflops"], "peak": peak, "unit": "TFLOP/s",
-                        "frac": round(r["tflops"] / peak, 4), "traffic": None,
+                        "frac": round(r["tflops"] / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                        "algorithmic_bytes_per_launch": round(kern[top]["bytes"] / kern[top]["launches"], 1),
                         "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                         "avg_launch_ms": round(r["ms_per_step"] / n_l, 4),
                         "algorithmic_gflop_per_launch": round(kern[top]["flops"] / kern[top]["launches"] / 1e9, 2),
@@ -356,7 +392,8 @@ def run_ours(args):
         else:
             peak = peaks["hbm_gbs"]
             roofline = {"kernel": top, "bound": "hbm", "achieved": r["gbs"], "peak": peak, "unit": "GB/s",
-                        "frac": round(r["gbs"] / peak, 4), "traffic": None, "peak_source": peaks["source"],
+                        "frac": round(r["gbs"] / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                        "peak_source": peaks["source"],
                         "avg_launch_ms": round(r["ms_per_step"] / n_l, 4),
                         "algorithmic_mb_per_launch": round(kern[top]["bytes"] / kern[top]["launches"] / 1e6, 2)}
     conv_ms = sum(v["ms_per_step"] for k, v in fam_rows.items() if "gemm" in k or "wgrad" in k)
@@ -394,7 +431,8 @@ def run_ours(args):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
