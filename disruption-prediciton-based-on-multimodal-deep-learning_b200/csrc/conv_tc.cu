@@ -40,6 +40,9 @@ struct TcParams {
   int sub_row_bytes, tap_sub_stride, red_C;
   int Ntile;
   int a_box_bytes, b_box_bytes, b_sub_bytes, stage_bytes, num_stages;
+  int lps, slot_bytes;      // loads per pipeline stage; bytes of one load's slot (stage_bytes = lps * slot_bytes)
+  int reg_stats;            // BN statistics accumulated in epilogue registers
+  int drain_rs;             // unrolled drain: chunks of 16 channels per epilogue warp (0 = generic loop)
   int w_resident, off_wgt;  // all weight blocks loaded once per CTA instead of once per stage
   int mma_stats, stat_M, acc_bufs;  // BN statistics accumulated in TMEM by the tensor core
   // staging tile (epilogue -> TMA store, and B operand of the statistics MMAs): chunks of cw channels, swizzled
@@ -48,6 +51,7 @@ struct TcParams {
   int off_staging, off_ones, off_stats, off_scratch, off_bars;
   int tmem_cols, layout_type, sbo_bytes;
   int has_stats, has_addend;
+  int dbg_skip;  // development: 1 = no epilogue data movement / stores, 2 = no TMA loads, 4 = one MMA per load
   long long a_off, a_sw, a_sh, a_st, a_sb;  // addend view: element offset / strides of (w,h,t,b) in the dst tensor
   signed char off_w[TC_MAX_LOADS], off_h[TC_MAX_LOADS], off_t[TC_MAX_LOADS];
   short tap0[TC_MAX_LOADS];
@@ -75,6 +79,19 @@ struct TileIter {
   }
 };
 
+// Named barriers (bar.sync / bar.arrive) hand tiles between the epilogue warps, the TMA-store warp and the MMA warp:
+// a named-barrier hop costs ~40 cycles on B200 while every mbarrier operation (arrive or try_wait, even on a completed
+// phase) occupies its thread for ~180-230 cycles (scripts/ubench/sync_ops.cu).  mbarriers remain only where the
+// hardware requires them (TMA completion, tcgen05.commit), and the TMA pipeline moves `lps` loads per stage so that
+// one wait / one expect_tx / one commit covers a whole tile's worth of operands where shared memory allows.
+constexpr int BAR_SREADY = 3;   // +buf : epilogue (arrive) -> store warp (sync): staged tile complete
+constexpr int BAR_SFREE = 5;    // +buf : store warp (arrive) -> epilogue (sync): staging buffer may be overwritten
+constexpr int BAR_TEMPTY = 7;   // +acc : epilogue (arrive) -> MMA warp (sync): TMEM accumulator drained
+constexpr int BAR_HANDOFF = TC_EPI + 32;
+
+// RS > 0: unrolled accumulator drain, <= RS chunks of 16 channels per epilogue warp; STATS: BN statistics accumulated in
+// registers from the fp32 accumulators (RS <= 3)
+template <int RS, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmD, const __grid_constant__ TcParams p,
@@ -90,11 +107,9 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   auto full_bar = [&](int i) { return bars + 8u * i; };
   auto empty_bar = [&](int i) { return bars + 8u * (S + i); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
   const uint32_t wbar = bars + 8u * (2 * S + 4);
-  auto sready_bar = [&](int b) { return bars + 8u * (2 * S + 5 + b); };
+  auto sready_bar = [&](int b) { return bars + 8u * (2 * S + 5 + b); };   // statistics-MMA mode only
   auto sdone_bar = [&](int b) { return bars + 8u * (2 * S + 7 + b); };
-  auto sfree_bar = [&](int b) { return bars + 8u * (2 * S + 9 + b); };
   const uint32_t tmem_slot = bars + 8u * (2 * S + 11);
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.off_bars + 8 * (2 * S + 11));
   float* stats_sm = reinterpret_cast<float*>(sm + p.off_stats);
@@ -106,8 +121,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tma_prefetch_desc(&tmD);
     for (int i = 0; i < S; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI);
-      mbar_init(sready_bar(a), TC_EPI); mbar_init(sdone_bar(a), 1); mbar_init(sfree_bar(a), 1);
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(sready_bar(a), TC_EPI); mbar_init(sdone_bar(a), 1);
     }
     mbar_init(wbar, 1);
     mbar_fence_init();
@@ -118,7 +133,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   if (threadIdx.x >= TC_THREADS - TC_EPI) {
     const int e0 = threadIdx.x - (TC_THREADS - TC_EPI);
-    if (p.has_stats && !p.mma_stats)
+    if (p.has_stats && !p.mma_stats && !STATS)
       for (int i = e0; i < 2 * p.dC; i += TC_EPI) stats_sm[i] = 0.f;
     if (p.mma_stats) {   // the all-ones A operand of the column-sum MMA (any canonical layout: every element is 1)
       uint32_t* ones = reinterpret_cast<uint32_t*>(sm + p.off_ones);
@@ -133,6 +148,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only below
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t col_g = (uint32_t)(p.acc_bufs * p.Ntile), col_s = col_g + (uint32_t)p.Ntile;
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int TL = p.nloads * p.ncblk;   // loads per tile, moved `lps` per pipeline stage
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -154,23 +171,30 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti.next()) {
       const int n_idx = ti.n, b = ti.b;
       const int w0 = ti.w * p.bw * p.mw, h0 = ti.h * p.bh * p.mh, t0 = ti.t * p.bt * p.mt;
-      for (int l = 0; l < p.nloads; ++l) {
-        for (int cb = 0; cb < p.ncblk; ++cb) {
-          const long long c0 = dbg ? clock64() : 0;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (dbg) w_prod += clock64() - c0;
-          const uint32_t sa = sbase + (uint32_t)stage * p.stage_bytes;
-          mbar_expect_tx(full_bar(stage), tx);
-          tma_load_5d(&tmA, full_bar(stage), sa, cb * p.CB, w0 + p.off_w[l], h0 + p.off_h[l], t0 + p.off_t[l], b);
-          if (!p.w_resident) {
-            for (int s = 0; s < p.nsub; ++s) {
-              const int tap = p.tap0[l] + s * p.tap_sub_stride;
-              tma_load_2d(&tmB, full_bar(stage), sa + p.stage_bytes - (p.nsub - s) * p.b_sub_bytes,
-                          tap * p.red_C + cb * p.CB, n_idx * p.Ntile);
+      int l = 0, cb = 0;
+      for (int base = 0; base < TL; base += p.lps) {
+        const int cnt = min(p.lps, TL - base);
+        const long long c0 = dbg ? clock64() : 0;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (dbg) w_prod += clock64() - c0;
+        if (p.dbg_skip & 2) {
+          mbar_arrive(full_bar(stage));
+        } else {
+          mbar_expect_tx(full_bar(stage), (uint32_t)cnt * tx);
+          uint32_t sa = sbase + (uint32_t)stage * p.stage_bytes;
+          for (int j = 0; j < cnt; ++j, sa += p.slot_bytes) {
+            tma_load_5d(&tmA, full_bar(stage), sa, cb * p.CB, w0 + p.off_w[l], h0 + p.off_h[l], t0 + p.off_t[l], b);
+            if (!p.w_resident) {
+              for (int s = 0; s < p.nsub; ++s) {
+                const int tap = p.tap0[l] + s * p.tap_sub_stride;
+                tma_load_2d(&tmB, full_bar(stage), sa + p.slot_bytes - (p.nsub - s) * p.b_sub_bytes,
+                            tap * p.red_C + cb * p.CB, n_idx * p.Ntile);
+              }
             }
+            if (++cb == p.ncblk) { cb = 0; ++l; }
           }
-          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
+        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
     if (dbg) { dbg[blockIdx.x * 8 + 0] = w_prod; dbg[blockIdx.x * 8 + 1] = clock64() - t_start; }
@@ -179,13 +203,14 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t idesc = make_idesc_bf16(128, p.Ntile, 0, 0);
     const uint32_t hi = smem_desc_hi((uint32_t)p.sbo_bytes, (uint32_t)p.layout_type);
     const uint32_t a_sub = (uint32_t)p.sub_row_bytes >> 4, b_sub = (uint32_t)p.b_sub_bytes >> 4;
-    const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
+    const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, slot16 = (uint32_t)p.slot_bytes >> 4;
     const uint32_t lo0 = smem_desc_lo(sbase, 16);
     const uint32_t wlo0 = smem_desc_lo(sbase + (uint32_t)p.off_wgt, 16);
-    const uint32_t b_off0 = stage16 - (uint32_t)p.nsub * b_sub;
-    const int ksteps_full = p.CB >> 4, ncblk = p.ncblk, nsub = p.nsub;
+    const uint32_t b_off0 = slot16 - (uint32_t)p.nsub * b_sub;
+    const int ksteps_full = p.CB >> 4, ncblk = p.ncblk, nsub = p.nsub, lps = p.lps;
     const bool resident = p.w_resident != 0;
     const uint32_t b_step = resident ? (uint32_t)ncblk * b_sub : b_sub;
+    const uint32_t w_tap = (uint32_t)(nsub * ncblk) * b_sub;
     // statistics MMAs: D_g += Y^T Y (diagonal = sum of squares), D_s += 1^T Y (column sums); Y = staged bf16 tile
     const uint32_t st_hi = smem_desc_hi((uint32_t)(8 * p.st_rowbytes), (uint32_t)p.st_layout);
     const uint32_t st_lo0 = smem_desc_lo(sbase + (uint32_t)p.off_staging, (uint32_t)p.st_chunk_bytes);
@@ -219,40 +244,48 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (resident) { mbar_wait(wbar, 0u); tc_fence_after(); }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       long long c0 = dbg ? clock64() : 0;
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      if (it >= p.acc_bufs) named_bar_sync(BAR_TEMPTY + acc, BAR_HANDOFF);   // epilogue drained this accumulator
       if (dbg) w_te += clock64() - c0;
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Ntile);
       uint32_t accumulate = 0;
       uint32_t w_lo = wlo0;
-      for (int l = 0; l < p.nloads; ++l) {
-        for (int cb = 0; cb < ncblk; ++cb) {
-          const int ksteps = (cb == ncblk - 1) ? p.ksteps_last : ksteps_full;
-          c0 = dbg ? clock64() : 0;
-          mbar_wait(full_bar(stage), phase);
-          if (dbg) w_full += clock64() - c0;
-          tc_fence_after();
-          if (leader) {
-            uint32_t a_lo = lo0 + (uint32_t)stage * stage16;
-            uint32_t b_lo = resident ? (w_lo + (uint32_t)cb * b_sub) : (a_lo + b_off0);
+      int cb = 0;
+      for (int base = 0; base < TL; base += lps) {
+        const int cnt = min(lps, TL - base);
+        c0 = dbg ? clock64() : 0;
+        mbar_wait(full_bar(stage), phase);
+        if (dbg) w_full += clock64() - c0;
+        tc_fence_after();
+        if (leader) {
+          uint32_t a_slot = lo0 + (uint32_t)stage * stage16;
+          uint32_t w_l = w_lo;
+          int c = cb;
+          uint32_t accum = accumulate;
+          for (int j = 0; j < cnt; ++j, a_slot += slot16) {
+            const int ksteps = (c == ncblk - 1) ? p.ksteps_last : ksteps_full;
+            uint32_t a_lo = a_slot;
+            uint32_t b_lo = resident ? (w_l + (uint32_t)c * b_sub) : (a_slot + b_off0);
             for (int s = 0; s < nsub; ++s) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                if (k < ksteps) {
-                  umma_bf16_lh(tmem_d, a_lo + 2u * k, hi, b_lo + 2u * k, hi, idesc, accumulate);
-                  accumulate = 1;
+                if (k < ksteps && !((p.dbg_skip & 4) && (k > 0 || s > 0))) {
+                  umma_bf16_lh(tmem_d, a_lo + 2u * k, hi, b_lo + 2u * k, hi, idesc, accum);
+                  accum = 1;
                 }
               }
               a_lo += a_sub;
               b_lo += b_step;
             }
-            umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+            if (++c == ncblk) { c = 0; w_l += w_tap; }
           }
-          __syncwarp();
-          accumulate = 1;
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
         }
-        w_lo += (uint32_t)(nsub * ncblk) * b_sub;
+        __syncwarp();
+        accumulate = 1;
+        cb += cnt;
+        while (cb >= ncblk) { cb -= ncblk; w_lo += w_tap; }
+        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
       if (leader) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
       __syncwarp();
@@ -261,31 +294,30 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     if (p.mma_stats && it > 0) issue_stats(it - 1);
     if (dbg && lane == 0) { dbg[blockIdx.x * 8 + 2] = w_full; dbg[blockIdx.x * 8 + 3] = w_te; dbg[blockIdx.x * 8 + 4] = clock64() - t_start; }
-  } else if (warp == 3 && lane == 0) {
-    // ===================== TMA store issuer: staged tile -> global, off the epilogue's critical path ==========
+  } else if (warp == 3) {
+    // ===================== TMA store warp: staged tile -> global, off the epilogue's critical path ==========
     const int nst = (p.Ntile + p.cw - 1) / p.cw;
-    int it = 0, prev_buf = -1;
+    int it = 0;
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, ti.next()) {
-      const int n_idx = ti.n, tw = ti.w, th = ti.h, tt = ti.t, b = ti.b;
       const int buf = it % p.st_bufs;
-      mbar_wait(sready_bar(buf), (uint32_t)((it / p.st_bufs) & 1));
-      const uint32_t staging_s = sbase + (uint32_t)(p.off_staging + buf * p.st_buf_bytes);
-      for (int ch = 0; ch < nst; ++ch)
-        tma_store_5d(&tmD, staging_s + (uint32_t)(ch * p.st_chunk_bytes), n_idx * p.Ntile + ch * p.cw, tw * p.bw,
-                     th * p.bh, tt * p.bt, b);
-      tma_store_commit();
-      if (p.st_bufs == 2) {
-        tma_store_wait_read1();                       // the previous tile's store has finished reading its buffer
-        if (prev_buf >= 0) mbar_arrive(sfree_bar(prev_buf));
-        prev_buf = buf;
-      } else {
-        tma_store_wait_read();
-        mbar_arrive(sfree_bar(buf));
+      named_bar_sync(BAR_SREADY + buf, BAR_HANDOFF);
+      if (lane == 0) {
+        const uint32_t staging_s = sbase + (uint32_t)(p.off_staging + buf * p.st_buf_bytes);
+        for (int ch = 0; ch < nst && !(p.dbg_skip & 1); ++ch)
+          tma_store_5d(&tmD, staging_s + (uint32_t)(ch * p.st_chunk_bytes), ti.n * p.Ntile + ch * p.cw, ti.w * p.bw,
+                       ti.h * p.bh, ti.t * p.bt, ti.b);
+        tma_store_commit();
+        if (p.st_bufs == 2) tma_store_wait_read1();   // the previous tile's store has finished reading its buffer
+        else tma_store_wait_read();
       }
+      __syncwarp();
+      // release the buffer whose store has been read, if a later tile will use it
+      const int done_it = p.st_bufs == 2 ? it - 1 : it;
+      if (done_it >= 0 && done_it + p.st_bufs < my_tiles) named_bar_arrive(BAR_SFREE + (done_it % p.st_bufs), BAR_HANDOFF);
     }
-    tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> bf16 -> swizzled staging tile =====================
     const int et = threadIdx.x - (TC_THREADS - TC_EPI);  // 0..255
@@ -297,12 +329,20 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int lw = e % p.bw, lh = (e / p.bw) % p.bh, lt = e / (p.bw * p.bh);
     const uint32_t row_off = (uint32_t)(e * p.st_rowbytes);
     const uint32_t st_mask = (uint32_t)p.st_mask;
-    const bool legacy_stats = p.has_stats && !p.mma_stats;
+    const bool legacy_stats = p.has_stats && !p.mma_stats && !STATS;
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
     long long w_tf = 0, w_a = 0, w_b = 0, w_c = 0, w_d = 0;
     const long long t_start = dbg ? clock64() : 0;
+    constexpr int NS = STATS ? RS : 1;
+    float ssum[NS][16], ssq[NS][16];   // per-thread (one pixel row) channel sums over all tiles
+    if (STATS) {
+#pragma unroll
+      for (int j = 0; j < NS; ++j)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { ssum[j][k] = 0.f; ssq[j][k] = 0.f; }
+    }
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, ti.next()) {
@@ -310,7 +350,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int w = ti.w * p.bw + lw, h = ti.h * p.bh + lh, t = ti.t * p.bt + lt;
       const bool valid = (w < p.dW) && (h < p.dH) && (t < p.dT);
       const __nv_bfloat16* arow = nullptr;
-      if (p.has_addend && valid)
+      if (!STATS && p.has_addend && valid)
         arow = addend + p.a_off + (int64_t)b * p.a_sb + (int64_t)t * p.a_st + (int64_t)h * p.a_sh + (int64_t)w * p.a_sw +
                n_idx * p.Ntile;
       const int buf = it % p.st_bufs;
@@ -321,25 +361,16 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (dbg) w_tf += clock64() - c0;
       long long c1 = dbg ? clock64() : 0;
       tc_fence_after();
-      // the staging buffer is free once the TMA store issued st_bufs tiles ago has read it and (statistics) the
+      // the staging buffer is free once the TMA store issued st_bufs tiles ago has read it and (statistics MMAs) the
       // MMAs over it have retired
       if (it >= p.st_bufs) {
-        const uint32_t par = (uint32_t)(((it / p.st_bufs) - 1) & 1);
-        mbar_wait(sfree_bar(buf), par);
-        if (p.mma_stats) mbar_wait(sdone_bar(buf), par);
+        named_bar_sync(BAR_SFREE + buf, BAR_HANDOFF);
+        if (p.mma_stats) mbar_wait(sdone_bar(buf), (uint32_t)(((it / p.st_bufs) - 1) & 1));
       }
       if (dbg) { const long long c2 = clock64(); w_a += c2 - c1; c1 = c2; }
 
       const uint32_t taddr = tmem_base + (uint32_t)(acc * p.Ntile) + ((uint32_t)(q * 32) << 16);
-      auto emit16 = [&](const uint32_t* v, int c) {   // 16 accumulator columns starting at channel c of this tile
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = valid ? __uint_as_float(v[j]) : 0.f;
-        if (arow != nullptr) {
-          const f8 a0 = ld8(arow + c), a1 = ld8(arow + c + 8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { f[j] += a0.v[j]; f[8 + j] += a1.v[j]; }
-        }
+      auto store16 = [&](const float* f, int c) {   // 16 consecutive channels starting at channel c of this tile
         uint4 o0, o1;
         __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
         __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
@@ -357,26 +388,77 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         *reinterpret_cast<uint4*>(cbase + off0) = o0;
         *reinterpret_cast<uint4*>(cbase + off1) = o1;
       };
-      for (int c0c = cbeg; c0c < cend; c0c += 64) {
-        // up to 64 columns in flight per wait (column counts are multiples of 16)
-        uint32_t va[32], vb[32];
-        const int rem = cend - c0c;
-        if (rem >= 32) tmem_ld32_nowait(taddr + (uint32_t)c0c, va); else tmem_ld16_nowait(taddr + (uint32_t)c0c, va);
-        if (rem >= 64) tmem_ld32_nowait(taddr + (uint32_t)c0c + 32u, vb);
-        else if (rem >= 48) tmem_ld16_nowait(taddr + (uint32_t)c0c + 32u, vb);
-        tmem_wait_ld16(va); tmem_wait_ld16(va + 16); tmem_wait_ld16(vb); tmem_wait_ld16(vb + 16);
-        emit16(va, c0c);
-        if (rem >= 32) emit16(va + 16, c0c + 16);
-        if (rem >= 48) emit16(vb, c0c + 32);
-        if (rem >= 64) emit16(vb + 16, c0c + 48);
+      auto emit16 = [&](const uint32_t* v, int c) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = valid ? __uint_as_float(v[j]) : 0.f;
+        if (arow != nullptr) {
+          const f8 a0 = ld8(arow + c), a1 = ld8(arow + c + 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { f[j] += a0.v[j]; f[8 + j] += a1.v[j]; }
+        }
+        store16(f, c);
+      };
+      if (RS > 0) {
+        // <= RS chunks of 16 columns: all TMEM loads in flight at once; statistics from the fp32 accumulators
+        if (!(p.dbg_skip & 1)) {
+          const int nch = (cend - cbeg) >> 4;
+#pragma unroll
+          for (int j0 = 0; j0 < (RS > 0 ? RS : 1); j0 += 2) {   // two chunks in flight per wait
+            uint32_t v[2][16];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+              if (j0 + jj < RS && j0 + jj < nch) tmem_ld16_nowait(taddr + (uint32_t)(cbeg + 16 * (j0 + jj)), v[jj]);
+            tmem_wait_ld16(v[0]); tmem_wait_ld16(v[1]);
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              if (j0 + jj < RS && j0 + jj < nch) {
+                float f[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) f[k] = valid ? __uint_as_float(v[jj][k]) : 0.f;
+                if (STATS) {
+                  constexpr int dummy = 0;
+                  const int js = (j0 + jj < NS) ? j0 + jj : dummy;
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) {
+                    ssum[js][k] += f[k];
+                    ssq[js][k] = fmaf(f[k], f[k], ssq[js][k]);
+                  }
+                }
+                if (!STATS && arow != nullptr) {
+                  const int c = cbeg + 16 * (j0 + jj);
+                  const f8 a0 = ld8(arow + c), a1 = ld8(arow + c + 8);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) { f[k] += a0.v[k]; f[8 + k] += a1.v[k]; }
+                }
+                store16(f, cbeg + 16 * (j0 + jj));
+              }
+            }
+          }
+        }
+      } else {
+        for (int c0c = cbeg; c0c < cend && !(p.dbg_skip & 1); c0c += 64) {
+          // up to 64 columns in flight per wait (column counts are multiples of 16)
+          uint32_t va[32], vb[32];
+          const int rem = cend - c0c;
+          if (rem >= 32) tmem_ld32_nowait(taddr + (uint32_t)c0c, va); else tmem_ld16_nowait(taddr + (uint32_t)c0c, va);
+          if (rem >= 64) tmem_ld32_nowait(taddr + (uint32_t)c0c + 32u, vb);
+          else if (rem >= 48) tmem_ld16_nowait(taddr + (uint32_t)c0c + 32u, vb);
+          tmem_wait_ld16(va); tmem_wait_ld16(va + 16); tmem_wait_ld16(vb); tmem_wait_ld16(vb + 16);
+          emit16(va, c0c);
+          if (rem >= 32) emit16(va + 16, c0c + 16);
+          if (rem >= 48) emit16(vb, c0c + 32);
+          if (rem >= 64) emit16(vb + 16, c0c + 48);
+        }
       }
       if (dbg) { const long long c2 = clock64(); w_b += c2 - c1; c1 = c2; }
       // accumulator drained: hand the TMEM buffer back to the MMA warp; publish the staged tile to the async proxy
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      if (it + p.acc_bufs < my_tiles) named_bar_arrive(BAR_TEMPTY + acc, BAR_HANDOFF);
       fence_proxy_async_smem();
       if (legacy_stats) named_bar_sync(1, TC_EPI);
-      mbar_arrive(sready_bar(buf));     // 128 arrivals: TMA-store warp (and the statistics MMAs) may read the tile
+      named_bar_arrive(BAR_SREADY + buf, BAR_HANDOFF);   // the TMA-store warp may read the tile
+      if (p.mma_stats) mbar_arrive(sready_bar(buf));     // ... and so may the statistics MMAs
       if (dbg) { const long long c2 = clock64(); w_c += c2 - c1; c1 = c2; }
       if (legacy_stats) {
         // fallback (N tiles > 1): per-channel sum / sum of squares of the bf16 tile from the (unswizzled) staging tile
@@ -417,9 +499,9 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           stats_sm[n_idx * p.Ntile + c] += a0;
           stats_sm[p.dC + n_idx * p.Ntile + c] += b0;
         }
-        // legacy statistics read the tile in place: it may only be re-used (sfree) after these reads; with one
-        // staging buffer the next tile's drain waits for sfree, which the store warp signals after ITS read, and the
-        // named barriers above order the readers before any thread can pass the next sready arrival
+        // legacy statistics read the tile in place: the store warp releases the buffer (BAR_SFREE) only after ITS read,
+        // and the named barriers above order these readers before any thread can start the next drain into it
+        named_bar_sync(2, TC_EPI);
       }
       if (dbg) { const long long c2 = clock64(); w_d += c2 - c1; c1 = c2; }
       if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1u; }
@@ -428,6 +510,30 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       dbg[blockIdx.x * 8 + 5] = w_tf; dbg[blockIdx.x * 8 + 6] = clock64() - t_start;
       long long* d2 = dbg + 148 * 8 + blockIdx.x * 8;
       d2[0] = w_a; d2[1] = w_b; d2[2] = w_c; d2[3] = w_d;
+    }
+    if (STATS) {
+      // rows -> channels: butterfly over the 32 pixel rows of the warp, then the 4 row quadrants through smem
+      const int nch = (cend - cbeg) >> 4;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float a0 = warp_sum(ssum[j][k]), b0 = warp_sum(ssq[j][k]);
+          if (lane == 0 && j < nch) {
+            scratch[(q * p.Ntile + cbeg + 16 * j + k) * 2 + 0] = a0;
+            scratch[(q * p.Ntile + cbeg + 16 * j + k) * 2 + 1] = b0;
+          }
+        }
+      }
+      named_bar_sync(1, TC_EPI);
+      float* prow = part + (int64_t)blockIdx.x * 2 * p.dC;
+      for (int c = et; c < p.Ntile; c += TC_EPI) {
+        float a0 = 0.f, b0 = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { a0 += scratch[(g * p.Ntile + c) * 2 + 0]; b0 += scratch[(g * p.Ntile + c) * 2 + 1]; }
+        prow[c] = a0;
+        prow[p.dC + c] = b0;
+      }
     }
     if (legacy_stats) {
       named_bar_sync(1, TC_EPI);
@@ -495,7 +601,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2;
+static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1;
 int tc_option(const char* name, int value, bool set) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_opt_halo;
@@ -506,6 +612,9 @@ int tc_option(const char* name, int value, bool set) {
   else if (!strcmp(name, "tc_resident")) slot = &g_opt_resident;
   else if (!strcmp(name, "tc_chunked")) slot = &g_opt_chunked;
   else if (!strcmp(name, "tc_st_bufs")) slot = &g_opt_st_bufs;
+  else if (!strcmp(name, "tc_dbg_skip")) slot = &g_opt_dbg_skip;
+  else if (!strcmp(name, "tc_lps_max")) slot = &g_opt_lps_max;
+  else if (!strcmp(name, "tc_reg_stats")) slot = &g_opt_reg_stats;
   if (slot == nullptr) return -1;
   if (set) *slot = value;
   return *slot;
@@ -567,8 +676,12 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
   // staging layout / statistics mode / resident weights
   const int used_taps = taps;
   p.has_stats = has_stats ? 1 : 0;
-  p.mma_stats = (has_stats && g_opt_mma_stats && p.n_ntiles == 1 && p.Ntile <= 128) ? 1 : 0;
-  const bool chunked = p.n_ntiles == 1 && (p.mma_stats || (!has_stats && g_opt_chunked));
+  // statistics: in epilogue registers from the fp32 accumulators (<= 3 chunks of 16 channels per epilogue warp), else
+  // on the tensor core (Gram + ones MMAs over the staged bf16 tile), else from the staged tile on the CUDA cores
+  p.reg_stats = (has_stats && g_opt_reg_stats && p.n_ntiles == 1 && p.Ntile <= 96) ? 1 : 0;
+  p.drain_rs = (!has_stats || p.reg_stats) ? ((p.Ntile >> 4) + 1) / 2 : 0;
+  p.mma_stats = (has_stats && !p.reg_stats && g_opt_mma_stats && p.n_ntiles == 1 && p.Ntile <= 128) ? 1 : 0;
+  const bool chunked = p.n_ntiles == 1 && (p.mma_stats || ((!has_stats || p.reg_stats) && g_opt_chunked));
   if (chunked) {
     p.cw = p.Ntile > 32 ? 64 : (p.Ntile == 32 ? 32 : 16);
     p.st_mask = p.cw == 64 ? 7 : (p.cw == 32 ? 3 : 1);
@@ -670,20 +783,29 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
     out->a_box[1] = p.bw; out->a_box[2] = p.bh; out->a_box[3] = p.bt + g.kt - 1;
   }
   p.a_box_bytes = rows_l * rowbytes;
-  p.stage_bytes = round_up(p.a_box_bytes, 1024) + (p.w_resident ? 0 : p.nsub * p.b_sub_bytes);
-  int stages = (TC_SMEM_MAX - fixed_bytes()) / p.stage_bytes;
-  if (stages < 4 && p.st_bufs == 2) {   // prefer pipeline depth over a second staging buffer
+  p.slot_bytes = round_up(p.a_box_bytes, 1024) + (p.w_resident ? 0 : p.nsub * p.b_sub_bytes);
+  int slots = (TC_SMEM_MAX - fixed_bytes()) / p.slot_bytes;
+  if (slots < 4 && p.st_bufs == 2) {   // prefer pipeline depth over a second staging buffer
     p.st_bufs = 1;
-    stages = (TC_SMEM_MAX - fixed_bytes()) / p.stage_bytes;
+    slots = (TC_SMEM_MAX - fixed_bytes()) / p.slot_bytes;
   }
-  if (stages < 3 && p.w_resident) {
+  if (slots < 3 && p.w_resident) {
     p.w_resident = 0;
-    p.stage_bytes = round_up(p.a_box_bytes, 1024) + p.nsub * p.b_sub_bytes;
-    stages = (TC_SMEM_MAX - fixed_bytes()) / p.stage_bytes;
+    p.slot_bytes = round_up(p.a_box_bytes, 1024) + p.nsub * p.b_sub_bytes;
+    slots = (TC_SMEM_MAX - fixed_bytes()) / p.slot_bytes;
   }
+  if (slots < 2) return false;
+  // several loads per pipeline stage (one mbarrier round trip covers all of them) while >= 3 stages stay in flight
+  const int total_loads = p.nloads * p.ncblk;
+  int lps = total_loads < g_opt_lps_max ? total_loads : g_opt_lps_max;
+  if (lps < 1) lps = 1;
+  while (lps > 1 && slots / lps < 3) --lps;
+  int stages = slots / lps;
   if (stages > g_opt_max_stages) stages = g_opt_max_stages;
   if (stages > 8) stages = 8;
   if (stages < 2) return false;
+  p.lps = lps;
+  p.stage_bytes = lps * p.slot_bytes;
   p.num_stages = stages;
   p.off_wgt = stages * p.stage_bytes;
   p.off_staging = p.off_wgt + (p.w_resident ? wgt_total : 0);
@@ -764,6 +886,7 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
              "tcgen05 conv: tensors must be 16-byte aligned");
   TcParams& p = plan.p;
   p.has_addend = addend != nullptr ? 1 : 0;
+  p.dbg_skip = g_opt_dbg_skip;
   const CUtensorMapSwizzle sw = p.CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                            : (p.CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap tmA, tmB, tmD;
@@ -785,16 +908,27 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
+  typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const __nv_bfloat16*, float*,
+                         long long*);
+  static KernFn const kerns[10] = {tc_gather_gemm_kernel<0, false>, tc_gather_gemm_kernel<1, true>, tc_gather_gemm_kernel<2, true>,
+                                   tc_gather_gemm_kernel<3, true>,  tc_gather_gemm_kernel<1, false>, tc_gather_gemm_kernel<2, false>,
+                                   tc_gather_gemm_kernel<3, false>, tc_gather_gemm_kernel<4, false>, tc_gather_gemm_kernel<5, false>,
+                                   tc_gather_gemm_kernel<8, false>};
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(tc_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+    for (int i = 0; i < 10 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
   });
   DP_REQUIRE(attr_err == cudaSuccess, DP_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s",
              cudaGetErrorString(attr_err));
-  launch_pdl(tc_gather_gemm_kernel, dim3(plan.grid), dim3(TC_THREADS), plan.smem, s, tmA, tmB, tmD, p, (const __nv_bfloat16*)addend, part,
-                                                               (g_dbg && g_dbg_slots >= (size_t)148 * 16) ? g_dbg : nullptr);
+  long long* dbg = (g_dbg && g_dbg_slots >= (size_t)148 * 16) ? g_dbg : nullptr;
+  int ki = 0;
+  if (p.reg_stats) ki = p.drain_rs;                                   // 1..3
+  else if (p.drain_rs >= 1 && p.drain_rs <= 5) ki = 3 + p.drain_rs;   // 4..8
+  else if (p.drain_rs >= 6 && p.drain_rs <= 8) ki = 9;
+  launch_pdl(kerns[ki], dim3(plan.grid), dim3(TC_THREADS), plan.smem, s, tmA, tmB, tmD, p, (const __nv_bfloat16*)addend, part, dbg);
   if (getenv("DP_DEBUG_PLAN"))
-    fprintf(stderr, "[tc_gather] dst %dx%dx%dx%d src C=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d CB=%d ncblk=%d Ntile=%d stages=%d stage_bytes=%d a_box=%d tiles=%d grid=%d\n",
-            g.dT, g.dH, g.dW, g.dC, g.sC, g.kt * g.kh * g.kw, p.bw, p.bh, p.bt, p.nloads, p.nsub, p.CB, p.ncblk, p.Ntile, p.num_stages,
+    fprintf(stderr, "[tc_gather] dst %dx%dx%dx%d src C=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d CB=%d ncblk=%d Ntile=%d stages=%d lps=%d stats=%d/%d stage_bytes=%d a_box=%d tiles=%d grid=%d\n",
+            g.dT, g.dH, g.dW, g.dC, g.sC, g.kt * g.kh * g.kw, p.bw, p.bh, p.bt, p.nloads, p.nsub, p.CB, p.ncblk, p.Ntile, p.num_stages, p.lps, p.reg_stats * 10 + p.drain_rs, p.mma_stats,
             p.stage_bytes, p.a_box_bytes, p.num_tiles, plan.grid);
   if (nparts != nullptr) *nparts = plan.grid;
   return check_launch("tc_gather_gemm_kernel");

@@ -45,11 +45,11 @@ struct WgParams {
   int stack, gpl, cbS, M_last;
   int n_mt, n_tg, lpg, nsplit, tiles_per_split, num_items;
   int cbX, cbD, chunksX, chunksD;
-  int x_chunk_bytes, d_chunk_bytes, x_slot_bytes, d_slot_bytes, x_slots, d_slots;
+  int x_chunk_bytes, d_chunk_bytes, x_slot_bytes, d_slot_bytes, stage_bytes, num_stages;
   int x_rowbytes, d_rowbytes, x_layout, d_layout;
   int x_shift_bytes, x_box_bytes, d_box_bytes;
   int N, tmem_cols;
-  int off_x, off_bars;
+  int off_bars;
   signed char off_w[WG_MAX_LOADS], off_h[WG_MAX_LOADS], off_t[WG_MAX_LOADS];
   short tap0[WG_MAX_LOADS];
 };
@@ -82,21 +82,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t sbase = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (sbase - raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int XS = p.x_slots, DS = p.d_slots;
+  const int S = p.num_stages;
   const uint32_t bars = sbase + p.off_bars;
-  auto x_full = [&](int i) { return bars + 8u * i; };
-  auto x_empty = [&](int i) { return bars + 8u * (XS + i); };
-  auto d_full = [&](int i) { return bars + 8u * (2 * XS + i); };
-  auto d_empty = [&](int i) { return bars + 8u * (2 * XS + DS + i); };
-  const uint32_t tfull = bars + 8u * (2 * XS + 2 * DS), tempty = tfull + 8u;
+  auto full_bar = [&](int i) { return bars + 8u * i; };
+  auto empty_bar = [&](int i) { return bars + 8u * (S + i); };
+  const uint32_t tfull = bars + 8u * (2 * S), tempty = tfull + 8u;
   const uint32_t tmem_slot = tempty + 8u;
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.off_bars + 8 * (2 * XS + 2 * DS + 2));
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.off_bars + 8 * (2 * S + 2));
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmD);
-    for (int i = 0; i < XS; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 1); }
-    for (int i = 0; i < DS; ++i) { mbar_init(d_full(i), 1); mbar_init(d_empty(i), 1); }
+    for (int i = 0; i < S; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
     mbar_init(tfull, 1);
     mbar_init(tempty, WG_EPI);
     mbar_fence_init();
@@ -114,8 +111,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    int xs = 0, ds = 0;
-    uint32_t xph = 0, dph = 0;
+    // one pipeline stage = the dy tile plus every x box of the item's tap group: every mbarrier operation occupies its
+    // thread for ~200 cycles on B200 (scripts/ubench/sync_ops.cu), so a tile costs ONE wait / expect_tx / commit round
+    int st = 0;
+    uint32_t ph = 0;
     long long w_prod = 0;
     const long long t_start = dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -124,6 +123,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int nX = p.swap ? it.nchunkM : p.chunksX;
       const int chanD = p.swap ? 0 : 128 * it.mtile;
       const int chanX = p.swap ? 128 * it.mtile : 0;
+      const uint32_t tx = (uint32_t)(nD * p.d_box_bytes + (it.l1 - it.l0) * nX * p.x_box_bytes);
       for (int tile = it.tile0; tile < it.tile1; ++tile) {
         int r = tile;
         const int tw = r % p.ntile_w; r /= p.ntile_w;
@@ -132,31 +132,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int b = r;
         const int w0 = tw * p.bw, h0 = th * p.bh, t0 = tt * p.bt;
         long long c0 = dbg ? clock64() : 0;
-        mbar_wait(d_empty(ds), dph ^ 1u);
+        mbar_wait(empty_bar(st), ph ^ 1u);
         if (dbg) w_prod += clock64() - c0;
-        const uint32_t da = sbase + (uint32_t)(ds * p.d_slot_bytes);
-        mbar_expect_tx(d_full(ds), (uint32_t)(nD * p.d_box_bytes));
+        const uint32_t da = sbase + (uint32_t)(st * p.stage_bytes);
+        mbar_expect_tx(full_bar(st), tx);
         for (int j = 0; j < nD; ++j)
-          tma_load_5d(&tmD, d_full(ds), da + (uint32_t)(j * p.d_chunk_bytes), chanD + j * p.cbD, w0, h0, t0, b);
-        if (++ds == DS) { ds = 0; dph ^= 1u; }
-        for (int l = it.l0; l < it.l1; ++l) {
-          c0 = dbg ? clock64() : 0;
-          mbar_wait(x_empty(xs), xph ^ 1u);
-          if (dbg) w_prod += clock64() - c0;
-          const uint32_t xa = sbase + (uint32_t)(p.off_x + xs * p.x_slot_bytes);
-          mbar_expect_tx(x_full(xs), (uint32_t)(nX * p.x_box_bytes));
+          tma_load_5d(&tmD, full_bar(st), da + (uint32_t)(j * p.d_chunk_bytes), chanD + j * p.cbD, w0, h0, t0, b);
+        uint32_t xa = da + (uint32_t)p.d_slot_bytes;
+        for (int l = it.l0; l < it.l1; ++l, xa += (uint32_t)p.x_slot_bytes)
           for (int j = 0; j < nX; ++j)
-            tma_load_5d(&tmX, x_full(xs), xa + (uint32_t)(j * p.x_chunk_bytes), chanX + j * p.cbX,
+            tma_load_5d(&tmX, full_bar(st), xa + (uint32_t)(j * p.x_chunk_bytes), chanX + j * p.cbX,
                         w0 * p.mw + p.off_w[l], h0 * p.mh + p.off_h[l], t0 * p.mt + p.off_t[l], b);
-          if (++xs == XS) { xs = 0; xph ^= 1u; }
-        }
+        if (++st == S) { st = 0; ph ^= 1u; }
       }
     }
     if (dbg) { dbg[blockIdx.x * 8 + 0] = w_prod; dbg[blockIdx.x * 8 + 1] = clock64() - t_start; }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
-    int xs = 0, ds = 0;
-    uint32_t xph = 0, dph = 0, tph = 0;
+    int st = 0;
+    uint32_t ph = 0, tph = 0;
     // operand geometry: U = M side, V = N side
     const int u_rowbytes = p.swap ? p.x_rowbytes : p.d_rowbytes;
     const int v_rowbytes = p.swap ? p.d_rowbytes : p.x_rowbytes;
@@ -167,8 +161,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t u_step = (uint32_t)(16 * u_rowbytes) >> 4, v_step = (uint32_t)(16 * v_rowbytes) >> 4;
     const uint32_t x_shift16 = (uint32_t)p.x_shift_bytes >> 4;
     const uint32_t d_lo0 = smem_desc_lo(sbase, p.swap ? v_lbo : u_lbo);
-    const uint32_t x_lo0 = smem_desc_lo(sbase + (uint32_t)p.off_x, p.swap ? u_lbo : v_lbo);
-    const uint32_t d_slot16 = (uint32_t)p.d_slot_bytes >> 4, x_slot16 = (uint32_t)p.x_slot_bytes >> 4;
+    const uint32_t x_lo0 = smem_desc_lo(sbase + (uint32_t)p.d_slot_bytes, p.swap ? u_lbo : v_lbo);
+    const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, x_slot16 = (uint32_t)p.x_slot_bytes >> 4;
     const int ngrp = p.stack > 1 ? p.gpl : p.nsub;                          // MMA groups (accumulator blocks) per load
     const uint32_t x_adv16 = (uint32_t)(p.stack > 1 ? p.stack : 1) * x_shift16;
     const uint32_t N = (uint32_t)p.N;
@@ -183,21 +177,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_wait(tempty, tph ^ 1u);
       if (dbg) w_te += clock64() - c0;
       tc_fence_after();
+      const int nl = it.l1 - it.l0;
       for (int tile = it.tile0; tile < it.tile1; ++tile) {
         c0 = dbg ? clock64() : 0;
-        mbar_wait(d_full(ds), dph);
+        mbar_wait(full_bar(st), ph);
         if (dbg) w_full += clock64() - c0;
         tc_fence_after();
-        const uint32_t d_lo = d_lo0 + (uint32_t)ds * d_slot16;
-        const uint32_t first = (tile != it.tile0) ? 1u : 0u;
-        uint32_t tmem_d = tmem_base;
-        for (int l = it.l0; l < it.l1; ++l) {
-          c0 = dbg ? clock64() : 0;
-          mbar_wait(x_full(xs), xph);
-          if (dbg) w_full += clock64() - c0;
-          tc_fence_after();
-          if (leader) {
-            uint32_t x_lo = x_lo0 + (uint32_t)xs * x_slot16;
+        if (leader) {
+          const uint32_t d_lo = d_lo0 + (uint32_t)st * stage16;
+          const uint32_t first = (tile != it.tile0) ? 1u : 0u;
+          uint32_t tmem_d = tmem_base;
+          uint32_t x_slot = x_lo0 + (uint32_t)st * stage16;
+          for (int l = 0; l < nl; ++l, x_slot += x_slot16) {
+            uint32_t x_lo = x_slot;
             for (int g = 0; g < ngrp; ++g) {
               const uint32_t u_lo = p.swap ? x_lo : d_lo, v_lo = p.swap ? d_lo : x_lo;
               const uint32_t id = (g == ngrp - 1) ? idesc_last : idesc;
@@ -208,16 +200,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               x_lo += x_adv16;
               tmem_d += N;
             }
-            umma_commit(x_empty(xs));
-          } else {
-            tmem_d += N * (uint32_t)ngrp;
           }
-          __syncwarp();
-          if (++xs == XS) { xs = 0; xph ^= 1u; }
+          umma_commit(empty_bar(st));
         }
-        if (leader) umma_commit(d_empty(ds));
         __syncwarp();
-        if (++ds == DS) { ds = 0; dph ^= 1u; }
+        if (++st == S) { st = 0; ph ^= 1u; }
       }
       if (leader) umma_commit(tfull);
       __syncwarp();
@@ -479,15 +466,16 @@ static bool plan_wgrad(const dp_conv_desc* d, WgPlan* out) {
   const int bar_bytes = 1024;
   const int stack_pad = p.stack > 1 ? rup(p.stack * p.x_shift_bytes, 1024) : 0;
   const int avail = WG_SMEM_MAX - 1024 - bar_bytes - stack_pad;
-  p.d_slots = 3;
-  if (p.d_slots * p.d_slot_bytes + 2 * p.x_slot_bytes > avail) p.d_slots = 2;
-  int xs = (avail - p.d_slots * p.d_slot_bytes) / p.x_slot_bytes;
-  if (xs > 8) xs = 8;
-  if (xs < 2) return false;
-  p.x_slots = xs;
-  p.off_x = p.d_slots * p.d_slot_bytes;
+  // one stage = dy tile + the lpg x boxes of a tap group; shrink the tap group until two stages fit
+  while (p.lpg > 1 && 2 * (p.d_slot_bytes + p.lpg * p.x_slot_bytes) > avail) --p.lpg;
+  p.n_tg = (p.nloads + p.lpg - 1) / p.lpg;
+  p.stage_bytes = p.d_slot_bytes + p.lpg * p.x_slot_bytes;
+  int ns = avail / p.stage_bytes;
+  if (ns > 8) ns = 8;
+  if (ns < 2) return false;
+  p.num_stages = ns;
   // stacked MMAs read up to `stack` shifted windows: the junk window of a partial stack may run past the last slot
-  p.off_bars = p.off_x + p.x_slots * p.x_slot_bytes + stack_pad;
+  p.off_bars = p.num_stages * p.stage_bytes + stack_pad;
   out->smem = (size_t)p.off_bars + bar_bytes + 1024;
   if (out->smem > (size_t)WG_SMEM_MAX) return false;
 
@@ -569,9 +557,9 @@ int tc_conv_wgrad_view(const dp_conv_desc* d, const long long* xstrides, const v
   launch_pdl(wgrad_tc_kernel, dim3(plan.grid), dim3(WG_THREADS), plan.smem, s, tmX, tmD, p, (float*)ws,
                                                            (g_dbg && g_dbg_slots >= (size_t)plan.grid * 8) ? g_dbg : nullptr);
   if (getenv("DP_DEBUG_PLAN"))
-    fprintf(stderr, "[tc_wgrad] out %dx%dx%d Kp=%d Cp=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d swap=%d N=%d n_mt=%d n_tg=%d lpg=%d cbX=%d cbD=%d xslots=%d dslots=%d xslot=%d dslot=%d nsplit=%d tiles/split=%d grid=%d\n",
+    fprintf(stderr, "[tc_wgrad] out %dx%dx%d Kp=%d Cp=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d swap=%d N=%d n_mt=%d n_tg=%d lpg=%d cbX=%d cbD=%d stages=%d stage=%d xslot=%d dslot=%d nsplit=%d tiles/split=%d grid=%d\n",
             d->To, d->Ho, d->Wo, d->Kp, d->Cp, p.taps, p.bw, p.bh, p.bt, p.nloads, p.nsub, p.swap, p.N, p.n_mt, p.n_tg, p.lpg, p.cbX,
-            p.cbD, p.x_slots, p.d_slots, p.x_slot_bytes, p.d_slot_bytes, p.nsplit, p.tiles_per_split, plan.grid);
+            p.cbD, p.num_stages, p.stage_bytes, p.x_slot_bytes, p.d_slot_bytes, p.nsplit, p.tiles_per_split, plan.grid);
   rc = check_launch("wgrad_tc_kernel");
   if (rc != DP_OK) return rc;
   return wgrad_reduce_launch((const float*)ws, dw, p.nsplit, d->K, d->C, d->Kp, d->Cp, p.taps, s);

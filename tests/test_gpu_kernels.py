@@ -184,9 +184,13 @@ def _tc_check(geom, B, seed=0):
         assert torch.isfinite(y.float()).all(), "tc fwd left unwritten (NaN) output elements"
         assert (y[..., K:] == 0).all(), "padded output channels must be exactly zero"
         st = part[:nparts.value].double().sum(0)
-        yb = yo.double()   # statistics are taken from the bf16-rounded tile
-        res["sum"] = rel_err(st[0, :K], yb.sum(dim=(0, 2, 3, 4)))
-        res["sq"] = rel_err(st[1, :K], (yb * yb).sum(dim=(0, 2, 3, 4)))
+        # statistics come from the fp32 accumulators (register mode) or from the bf16-rounded tile (tensor-core / CUDA-core
+        # modes): they must match the fp64 convolution, or the rounded output, on the scale of sum|y| (zero-mean sums cancel)
+        def stat_err(yy):
+            yy = yy.double()
+            e_sum = float((st[0, :K] - yy.sum(dim=(0, 2, 3, 4))).abs().max() / yy.abs().sum(dim=(0, 2, 3, 4)).max())
+            return e_sum, rel_err(st[1, :K], (yy * yy).sum(dim=(0, 2, 3, 4)))
+        res["sum"], res["sq"] = min(stat_err(ref["y"]), stat_err(yo), key=lambda e: e[0] + e[1])
         assert res["fwd"] < 2 ** -7, res
         assert res["sum"] < 1e-3 and res["sq"] < 1e-3, res
     if lib.dp_conv_supported(C.byref(d), 1, L.IMPL_TC):
