@@ -357,6 +357,13 @@ def run_ours(args):
             step(x_dev[i % n_host], y_dev)
         if rank == 0:
             kern = Fn.PROFILER.summary()
+            if os.environ.get("DP_BENCH_DUMP"):     # per-launch list of the last profiled step (development aid)
+                recs = Fn.PROFILER.records
+                n = len(recs) // max(1, args.profile_steps)
+                with open(os.environ["DP_BENCH_DUMP"], "w") as f:
+                    for fam, fl, nb, a, b in recs[-n:]:
+                        ms = a.elapsed_time(b)
+                        f.write(f"{fam:20s} {ms*1e3:9.1f} us  {fl/ms/1e9 if ms > 0 else 0:8.1f} TF/s {nb/ms/1e6 if ms > 0 else 0:8.1f} GB/s  {nb/1e6:9.1f} MB\n")
             Fn.PROFILER = None
         barrier()
 

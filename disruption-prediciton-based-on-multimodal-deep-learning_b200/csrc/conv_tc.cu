@@ -40,8 +40,13 @@ struct TcParams {
   int sub_row_bytes, tap_sub_stride, red_C;
   int Ntile;
   int a_box_bytes, b_box_bytes, b_sub_bytes, stage_bytes, num_stages;
-  int lps, slot_bytes;      // loads per pipeline stage; bytes of one load's slot (stage_bytes = lps * slot_bytes)
+  int lps, slot_bytes;      // loads per pipeline stage; bytes of one full-width load's slot
+  // narrow tail block: the last channel block of a source with C % 64 in {16, 32} is loaded as a CBt-wide box with its own
+  // swizzle instead of a zero-filled 64-wide one (C = 80: 37 % less smem fill and L2 traffic)
+  int CBt, a_box_bytes_t, slot_bytes_t, layout_t, sbo_bytes_t, sub_row_bytes_t, unit_mode;
+  int b_box_bytes_t, b_sub_bytes_t, w_row_bytes;   // resident weights: compact tail block; bytes of one (load, sub-tap) row
   int reg_stats;            // BN statistics accumulated in epilogue registers
+  int dual_mma;             // two MMA-issuing warps on alternate tiles
   int drain_rs;             // unrolled drain: chunks of 16 channels per epilogue warp (0 = generic loop)
   int w_resident, off_wgt;  // all weight blocks loaded once per CTA instead of once per stage
   int mma_stats, stat_M, acc_bufs;  // BN statistics accumulated in TMEM by the tensor core
@@ -94,7 +99,8 @@ constexpr int BAR_HANDOFF = TC_EPI + 32;
 template <int RS, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const __grid_constant__ CUtensorMap tmD, const __grid_constant__ TcParams p,
+                      const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmA2,
+                      const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ TcParams p,
                       const __nv_bfloat16* __restrict__ addend, float* __restrict__ part, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -119,6 +125,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
+    if (p.CBt) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     for (int i = 0; i < S; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -153,64 +160,90 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    int stage = 0;
-    uint32_t phase = 0;
     long long w_prod = 0;
     const long long t_start = dbg ? clock64() : 0;
+    const int tailcb = p.CBt ? p.ncblk - 1 : -1;   // index of the narrow tail block (-1: none)
     if (p.w_resident) {
-      mbar_expect_tx(wbar, (uint32_t)(p.nloads * p.nsub * p.ncblk * p.b_box_bytes));
+      mbar_expect_tx(wbar, (uint32_t)(p.nloads * p.nsub * ((p.ncblk - (p.CBt ? 1 : 0)) * p.b_box_bytes + (p.CBt ? p.b_box_bytes_t : 0))));
       for (int l = 0; l < p.nloads; ++l)
         for (int s = 0; s < p.nsub; ++s)
           for (int cb = 0; cb < p.ncblk; ++cb)
-            tma_load_2d(&tmB, wbar, sbase + (uint32_t)(p.off_wgt + ((l * p.nsub + s) * p.ncblk + cb) * p.b_sub_bytes),
+            tma_load_2d(cb == tailcb ? &tmB2 : &tmB, wbar,
+                        sbase + (uint32_t)(p.off_wgt + (l * p.nsub + s) * p.w_row_bytes + cb * p.b_sub_bytes),
                         (p.tap0[l] + s * p.tap_sub_stride) * p.red_C + cb * p.CB, 0);
     }
-    const uint32_t tx = (uint32_t)(p.a_box_bytes + (p.w_resident ? 0 : p.nsub * p.b_box_bytes));
+    const uint32_t tx_w = (uint32_t)(p.w_resident ? 0 : p.nsub * p.b_box_bytes);
+    const uint32_t tx = (uint32_t)p.a_box_bytes + tx_w, tx_t = (uint32_t)(p.CBt ? p.a_box_bytes_t : p.a_box_bytes) + tx_w;
+    // dual mode: the stages form two private rings, one per MMA warp (tiles alternate), so that no mbarrier is ever
+    // waited on by two consumers in different phases (a parity wait cannot tell phase k+1 from phase k-1)
+    const int RN = p.dual_mma ? S / 2 : S;
+    int rstage0 = 0, rstage1 = 0;
+    uint32_t rphase0 = 0, rphase1 = 0;
+    int it = 0;
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti.next()) {
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti.next(), ++it) {
       const int n_idx = ti.n, b = ti.b;
       const int w0 = ti.w * p.bw * p.mw, h0 = ti.h * p.bh * p.mh, t0 = ti.t * p.bt * p.mt;
+      const int r = p.dual_mma ? (it & 1) : 0;
+      int stage = r ? rstage1 : rstage0;
+      uint32_t phase = r ? rphase1 : rphase0;
       int l = 0, cb = 0;
       for (int base = 0; base < TL; base += p.lps) {
         const int cnt = min(p.lps, TL - base);
+        const int sidx = r * RN + stage;
         const long long c0 = dbg ? clock64() : 0;
-        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_wait(empty_bar(sidx), phase ^ 1u);
         if (dbg) w_prod += clock64() - c0;
         if (p.dbg_skip & 2) {
-          mbar_arrive(full_bar(stage));
+          mbar_arrive(full_bar(sidx));
         } else {
-          mbar_expect_tx(full_bar(stage), (uint32_t)cnt * tx);
-          uint32_t sa = sbase + (uint32_t)stage * p.stage_bytes;
-          for (int j = 0; j < cnt; ++j, sa += p.slot_bytes) {
-            tma_load_5d(&tmA, full_bar(stage), sa, cb * p.CB, w0 + p.off_w[l], h0 + p.off_h[l], t0 + p.off_t[l], b);
+          {   // bytes of this stage: cnt loads starting at block cb, of which the tail blocks are narrow
+            const int ntail = (cb + cnt) / p.ncblk;   // each wrap of the block index passes the last block once
+            mbar_expect_tx(full_bar(sidx), (uint32_t)(cnt - ntail) * tx + (uint32_t)ntail * tx_t);
+          }
+          uint32_t sa = sbase + (uint32_t)sidx * p.stage_bytes;
+          for (int j = 0; j < cnt; ++j) {
+            const bool tail = cb == tailcb;
+            tma_load_5d(tail ? &tmA2 : &tmA, full_bar(sidx), sa, cb * p.CB, w0 + p.off_w[l], h0 + p.off_h[l], t0 + p.off_t[l], b);
+            const uint32_t sz = (uint32_t)((tail && p.unit_mode) ? p.slot_bytes_t : p.slot_bytes);
             if (!p.w_resident) {
               for (int s = 0; s < p.nsub; ++s) {
                 const int tap = p.tap0[l] + s * p.tap_sub_stride;
-                tma_load_2d(&tmB, full_bar(stage), sa + p.slot_bytes - (p.nsub - s) * p.b_sub_bytes,
+                tma_load_2d(&tmB, full_bar(sidx), sa + sz - (p.nsub - s) * p.b_sub_bytes,
                             tap * p.red_C + cb * p.CB, n_idx * p.Ntile);
               }
             }
+            sa += sz;
             if (++cb == p.ncblk) { cb = 0; ++l; }
           }
         }
-        if (++stage == S) { stage = 0; phase ^= 1u; }
+        if (++stage == RN) { stage = 0; phase ^= 1u; }
       }
+      if (r) { rstage1 = stage; rphase1 = phase; } else { rstage0 = stage; rphase0 = phase; }
     }
     if (dbg) { dbg[blockIdx.x * 8 + 0] = w_prod; dbg[blockIdx.x * 8 + 1] = clock64() - t_start; }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (warp == 2 && p.dual_mma)) {
     // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
+    // dual mode: warps 1 and 2 take alternate tiles (each owns one TMEM accumulator), so one warp issues MMAs while
+    // the other sits in the ~200-cycle mbarrier wait / tcgen05.commit latencies of its own tile
+    const int mw = p.dual_mma ? warp - 1 : 0, tstep = p.dual_mma ? 2 : 1;
+    const int RN = p.dual_mma ? S / 2 : S, rbase = mw * RN;   // this warp's private ring of stages
     const uint32_t idesc = make_idesc_bf16(128, p.Ntile, 0, 0);
     const uint32_t hi = smem_desc_hi((uint32_t)p.sbo_bytes, (uint32_t)p.layout_type);
     const uint32_t a_sub = (uint32_t)p.sub_row_bytes >> 4, b_sub = (uint32_t)p.b_sub_bytes >> 4;
     const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, slot16 = (uint32_t)p.slot_bytes >> 4;
+    const int tailcb = p.CBt ? p.ncblk - 1 : -1;
+    const uint32_t hi_t = smem_desc_hi((uint32_t)p.sbo_bytes_t, (uint32_t)p.layout_t);
+    const uint32_t a_sub_t = (uint32_t)p.sub_row_bytes_t >> 4;
+    const uint32_t slot16_t = (uint32_t)(p.unit_mode ? p.slot_bytes_t : p.slot_bytes) >> 4;
+    const uint32_t nsub_bsub = (uint32_t)p.nsub * ((uint32_t)p.b_sub_bytes >> 4);
     const uint32_t lo0 = smem_desc_lo(sbase, 16);
     const uint32_t wlo0 = smem_desc_lo(sbase + (uint32_t)p.off_wgt, 16);
-    const uint32_t b_off0 = slot16 - (uint32_t)p.nsub * b_sub;
     const int ksteps_full = p.CB >> 4, ncblk = p.ncblk, nsub = p.nsub, lps = p.lps;
     const bool resident = p.w_resident != 0;
-    const uint32_t b_step = resident ? (uint32_t)ncblk * b_sub : b_sub;
-    const uint32_t w_tap = (uint32_t)(nsub * ncblk) * b_sub;
+    const uint32_t b_step = resident ? (uint32_t)p.w_row_bytes >> 4 : b_sub;
+    const uint32_t w_tap = (uint32_t)nsub * ((uint32_t)p.w_row_bytes >> 4);
     // statistics MMAs: D_g += Y^T Y (diagonal = sum of squares), D_s += 1^T Y (column sums); Y = staged bf16 tile
     const uint32_t st_hi = smem_desc_hi((uint32_t)(8 * p.st_rowbytes), (uint32_t)p.st_layout);
     const uint32_t st_lo0 = smem_desc_lo(sbase + (uint32_t)p.off_staging, (uint32_t)p.st_chunk_bytes);
@@ -220,9 +253,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const bool leader = elect_one();   // the same lane issues every MMA and every commit
     int stage = 0;
     uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int it = 0;
+    int it = mw;
     long long w_full = 0, w_te = 0;
     const long long t_start = dbg ? clock64() : 0;
     auto issue_stats = [&](int j) {
@@ -242,7 +273,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       __syncwarp();
     };
     if (resident) { mbar_wait(wbar, 0u); tc_fence_after(); }
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (; it < my_tiles; it += tstep) {
+      const int acc = p.acc_bufs == 2 ? (it & 1) : 0;
       long long c0 = dbg ? clock64() : 0;
       if (it >= p.acc_bufs) named_bar_sync(BAR_TEMPTY + acc, BAR_HANDOFF);   // epilogue drained this accumulator
       if (dbg) w_te += clock64() - c0;
@@ -253,47 +285,52 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       int cb = 0;
       for (int base = 0; base < TL; base += lps) {
         const int cnt = min(lps, TL - base);
+        const int sidx = rbase + stage;
         c0 = dbg ? clock64() : 0;
-        mbar_wait(full_bar(stage), phase);
+        mbar_wait(full_bar(sidx), phase);
         if (dbg) w_full += clock64() - c0;
         tc_fence_after();
         if (leader) {
-          uint32_t a_slot = lo0 + (uint32_t)stage * stage16;
+          uint32_t a_slot = lo0 + (uint32_t)sidx * stage16;
           uint32_t w_l = w_lo;
           int c = cb;
           uint32_t accum = accumulate;
-          for (int j = 0; j < cnt; ++j, a_slot += slot16) {
+          for (int j = 0; j < cnt; ++j) {
+            const bool tail = c == tailcb;
             const int ksteps = (c == ncblk - 1) ? p.ksteps_last : ksteps_full;
+            const uint32_t sz = tail ? slot16_t : slot16;
+            const uint32_t a_hi = tail ? hi_t : hi, a_step = tail ? a_sub_t : a_sub;
+            const uint32_t b_hi = (tail && resident) ? hi_t : hi;   // streamed weights always arrive as full-width boxes
             uint32_t a_lo = a_slot;
-            uint32_t b_lo = resident ? (w_l + (uint32_t)c * b_sub) : (a_slot + b_off0);
+            uint32_t b_lo = resident ? (w_l + (uint32_t)c * b_sub) : (a_slot + sz - nsub_bsub);
             for (int s = 0; s < nsub; ++s) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (k < ksteps && !((p.dbg_skip & 4) && (k > 0 || s > 0))) {
-                  umma_bf16_lh(tmem_d, a_lo + 2u * k, hi, b_lo + 2u * k, hi, idesc, accum);
+                  umma_bf16_lh(tmem_d, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, accum);
                   accum = 1;
                 }
               }
-              a_lo += a_sub;
+              a_lo += a_step;
               b_lo += b_step;
             }
+            a_slot += sz;
             if (++c == ncblk) { c = 0; w_l += w_tap; }
           }
-          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+          umma_commit(empty_bar(sidx));  // frees the smem stage when these MMAs retire
         }
         __syncwarp();
         accumulate = 1;
         cb += cnt;
         while (cb >= ncblk) { cb -= ncblk; w_lo += w_tap; }
-        if (++stage == S) { stage = 0; phase ^= 1u; }
+        if (++stage == RN) { stage = 0; phase ^= 1u; }
       }
       if (leader) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
       __syncwarp();
-      if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1u; }
       if (p.mma_stats && it > 0) issue_stats(it - 1);
     }
     if (p.mma_stats && it > 0) issue_stats(it - 1);
-    if (dbg && lane == 0) { dbg[blockIdx.x * 8 + 2] = w_full; dbg[blockIdx.x * 8 + 3] = w_te; dbg[blockIdx.x * 8 + 4] = clock64() - t_start; }
+    if (dbg && lane == 0 && mw == 0) { dbg[blockIdx.x * 8 + 2] = w_full; dbg[blockIdx.x * 8 + 3] = w_te; dbg[blockIdx.x * 8 + 4] = clock64() - t_start; }
   } else if (warp == 3) {
     // ===================== TMA store warp: staged tile -> global, off the epilogue's critical path ==========
     const int nst = (p.Ntile + p.cw - 1) / p.cw;
@@ -601,7 +638,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1;
+static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1;
 int tc_option(const char* name, int value, bool set) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_opt_halo;
@@ -615,6 +652,8 @@ int tc_option(const char* name, int value, bool set) {
   else if (!strcmp(name, "tc_dbg_skip")) slot = &g_opt_dbg_skip;
   else if (!strcmp(name, "tc_lps_max")) slot = &g_opt_lps_max;
   else if (!strcmp(name, "tc_reg_stats")) slot = &g_opt_reg_stats;
+  else if (!strcmp(name, "tc_dual_mma")) slot = &g_opt_dual;
+  else if (!strcmp(name, "tc_tail")) slot = &g_opt_tail;
   if (slot == nullptr) return -1;
   if (set) *slot = value;
   return *slot;
@@ -668,11 +707,20 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
   p.ncblk = (g.sC + p.CB - 1) / p.CB;
   p.ksteps_last = (g.sC - (p.ncblk - 1) * p.CB) / 16;
   p.layout_type = p.CB == 64 ? 2 : (p.CB == 32 ? 4 : 6);
+  {
+    const int rem = g.sC - (p.ncblk - 1) * p.CB;
+    p.CBt = (g_opt_tail && p.ncblk > 1 && rem <= 32) ? (rem <= 16 ? 16 : 32) : 0;
+    p.layout_t = p.CBt == 32 ? 4 : 6;
+    p.sbo_bytes_t = 8 * p.CBt * 2;
+  }
   const int rowbytes = p.CB * 2;
   p.sbo_bytes = 8 * rowbytes;
   p.red_C = g.sC;
   p.b_box_bytes = p.Ntile * rowbytes;
   p.b_sub_bytes = round_up(p.b_box_bytes, 1024);
+  p.b_box_bytes_t = p.Ntile * p.CBt * 2;
+  p.b_sub_bytes_t = round_up(p.b_box_bytes_t, 1024);
+  p.w_row_bytes = (p.ncblk - (p.CBt ? 1 : 0)) * p.b_sub_bytes + (p.CBt ? p.b_sub_bytes_t : 0);
   // staging layout / statistics mode / resident weights
   const int used_taps = taps;
   p.has_stats = has_stats ? 1 : 0;
@@ -697,7 +745,7 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
   if (p.mma_stats && p.st_chunks < p.stat_M / p.cw) p.st_chunks = p.stat_M / p.cw;   // the Gram A operand spans stat_M channels
   p.st_buf_bytes = p.st_chunks * p.st_chunk_bytes;
   p.acc_bufs = (p.mma_stats && 4 * p.Ntile > 512) ? 1 : 2;
-  const int wgt_total = used_taps * p.ncblk * p.b_sub_bytes;
+  const int wgt_total = used_taps * p.w_row_bytes;
   p.w_resident = (g_opt_resident && p.n_ntiles == 1 && wgt_total <= 98304) ? 1 : 0;
   const int stats_bytes = round_up(2 * g.dC * 4, 16);
   const int misc = 2048 /*ones*/ + stats_bytes + 16384 /*scratch*/ + 256 /*barriers*/ + 1024 /*alignment*/;
@@ -783,29 +831,53 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
     out->a_box[1] = p.bw; out->a_box[2] = p.bh; out->a_box[3] = p.bt + g.kt - 1;
   }
   p.a_box_bytes = rows_l * rowbytes;
-  p.slot_bytes = round_up(p.a_box_bytes, 1024) + (p.w_resident ? 0 : p.nsub * p.b_sub_bytes);
-  int slots = (TC_SMEM_MAX - fixed_bytes()) / p.slot_bytes;
-  if (slots < 4 && p.st_bufs == 2) {   // prefer pipeline depth over a second staging buffer
-    p.st_bufs = 1;
-    slots = (TC_SMEM_MAX - fixed_bytes()) / p.slot_bytes;
-  }
-  if (slots < 3 && p.w_resident) {
-    p.w_resident = 0;
-    p.slot_bytes = round_up(p.a_box_bytes, 1024) + p.nsub * p.b_sub_bytes;
-    slots = (TC_SMEM_MAX - fixed_bytes()) / p.slot_bytes;
-  }
-  if (slots < 2) return false;
-  // several loads per pipeline stage (one mbarrier round trip covers all of them) while >= 3 stages stay in flight
+  p.a_box_bytes_t = rows_l * p.CBt * 2;
+  p.sub_row_bytes_t = p.sub_row_bytes / rowbytes * p.CBt * 2;
+  auto set_slots = [&]() {
+    const int wb = p.w_resident ? 0 : p.nsub * p.b_sub_bytes;
+    p.slot_bytes = round_up(p.a_box_bytes, 1024) + wb;
+    p.slot_bytes_t = p.CBt ? round_up(p.a_box_bytes_t, 1024) + wb : p.slot_bytes;
+  };
+  set_slots();
+  // pipeline shape: `lps` loads per stage (one mbarrier round trip covers all of them).  When lps is a multiple of the
+  // block count a stage holds whole load units and the narrow tail block also takes a narrow slot.
   const int total_loads = p.nloads * p.ncblk;
-  int lps = total_loads < g_opt_lps_max ? total_loads : g_opt_lps_max;
-  if (lps < 1) lps = 1;
-  while (lps > 1 && slots / lps < 3) --lps;
-  int stages = slots / lps;
-  if (stages > g_opt_max_stages) stages = g_opt_max_stages;
-  if (stages > 8) stages = 8;
-  if (stages < 2) return false;
-  p.lps = lps;
-  p.stage_bytes = lps * p.slot_bytes;
+  auto stage_bytes_for = [&](int lps) {
+    return (lps % p.ncblk == 0) ? (lps / p.ncblk) * ((p.ncblk - 1) * p.slot_bytes + p.slot_bytes_t) : lps * p.slot_bytes;
+  };
+  int best_lps = 0, best_stages = 0;
+  auto search = [&]() {
+    long best_score = -1;
+    best_lps = 0;
+    const int avail = TC_SMEM_MAX - fixed_bytes();
+    for (int lps = 1; lps <= total_loads && lps <= (g_opt_lps_max < 1 ? 1 : g_opt_lps_max); ++lps) {
+      int st = avail / stage_bytes_for(lps);
+      if (st > g_opt_max_stages) st = g_opt_max_stages;
+      if (st > 8) st = 8;
+      if (st < 2) continue;
+      const int groups = (total_loads + lps - 1) / lps;
+      const bool dual_ok = g_opt_dual && p.acc_bufs == 2 && !p.mma_stats && st / 2 >= groups;
+      const long score = (dual_ok ? 1000000L : 0L) + ((st >= 3 || dual_ok) ? 100000L : 0L) + 100L * lps + st;
+      if (score > best_score) { best_score = score; best_lps = lps; best_stages = st; }
+    }
+  };
+  search();
+  if ((best_lps == 0 || best_stages < 3) && p.st_bufs == 2) {   // prefer pipeline depth over a second staging buffer
+    const int keep_lps = best_lps, keep_st = best_stages;
+    p.st_bufs = 1;
+    search();
+    if (best_lps == 0 || (keep_lps != 0 && best_stages <= keep_st)) { p.st_bufs = 2; best_lps = keep_lps; best_stages = keep_st; }
+  }
+  if (best_lps == 0 && p.w_resident) {
+    p.w_resident = 0;
+    set_slots();
+    search();
+  }
+  if (best_lps == 0) return false;
+  const int stages = best_stages;
+  p.lps = best_lps;
+  p.unit_mode = (p.lps % p.ncblk == 0) ? 1 : 0;
+  p.stage_bytes = stage_bytes_for(p.lps);
   p.num_stages = stages;
   p.off_wgt = stages * p.stage_bytes;
   p.off_staging = p.off_wgt + (p.w_resident ? wgt_total : 0);
@@ -818,6 +890,9 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
   while (cols < need_cols) cols <<= 1;
   if (cols > 512) return false;
   p.tmem_cols = cols;
+  // two MMA warps only when each private ring can hold a whole tile's stages (else the split rings lose prefetch depth)
+  const int groups = (p.nloads * p.ncblk + p.lps - 1) / p.lps;
+  p.dual_mma = (g_opt_dual && p.acc_bufs == 2 && !p.mma_stats && p.num_stages / 2 >= groups) ? 1 : 0;
   out->p = p;
   out->smem = (size_t)p.off_bars + 256 + 1024;
   const int sms = num_sms();
@@ -896,6 +971,15 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   const int taps = g.Kt * g.Kh * g.Kw;
   rc = encode_wgt_map(&tmB, wgt, taps * g.sC, g.dC, p.CB, p.Ntile, sw);
   if (rc != DP_OK) return rc;
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;
+  if (p.CBt) {
+    const CUtensorMapSwizzle swt = p.CBt == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    int tbox[5] = {p.CBt, plan.a_box[1], plan.a_box[2], plan.a_box[3], plan.a_box[4]};
+    rc = encode_act_map(&tmA2, src, g.sC, g.sW, g.sH, g.sT, g.B, tbox, plan.a_estride, swt, vstr);
+    if (rc != DP_OK) return rc;
+    rc = encode_wgt_map(&tmB2, wgt, taps * g.sC, g.dC, p.CBt, p.Ntile, swt);
+    if (rc != DP_OK) return rc;
+  }
   const int dbox[5] = {p.cw, p.bw, p.bh, p.bt, 1};
   p.a_sw = (long long)g.vs_w * g.dC;
   p.a_sh = (long long)g.vs_h * g.FW * g.dC;
@@ -908,7 +992,7 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
-  typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const __nv_bfloat16*, float*,
+  typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const __nv_bfloat16*, float*,
                          long long*);
   static KernFn const kerns[10] = {tc_gather_gemm_kernel<0, false>, tc_gather_gemm_kernel<1, true>, tc_gather_gemm_kernel<2, true>,
                                    tc_gather_gemm_kernel<3, true>,  tc_gather_gemm_kernel<1, false>, tc_gather_gemm_kernel<2, false>,
@@ -925,10 +1009,10 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   if (p.reg_stats) ki = p.drain_rs;                                   // 1..3
   else if (p.drain_rs >= 1 && p.drain_rs <= 5) ki = 3 + p.drain_rs;   // 4..8
   else if (p.drain_rs >= 6 && p.drain_rs <= 8) ki = 9;
-  launch_pdl(kerns[ki], dim3(plan.grid), dim3(TC_THREADS), plan.smem, s, tmA, tmB, tmD, p, (const __nv_bfloat16*)addend, part, dbg);
+  launch_pdl(kerns[ki], dim3(plan.grid), dim3(TC_THREADS), plan.smem, s, tmA, tmB, tmD, tmA2, tmB2, p, (const __nv_bfloat16*)addend, part, dbg);
   if (getenv("DP_DEBUG_PLAN"))
-    fprintf(stderr, "[tc_gather] dst %dx%dx%dx%d src C=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d CB=%d ncblk=%d Ntile=%d stages=%d lps=%d stats=%d/%d stage_bytes=%d a_box=%d tiles=%d grid=%d\n",
-            g.dT, g.dH, g.dW, g.dC, g.sC, g.kt * g.kh * g.kw, p.bw, p.bh, p.bt, p.nloads, p.nsub, p.CB, p.ncblk, p.Ntile, p.num_stages, p.lps, p.reg_stats * 10 + p.drain_rs, p.mma_stats,
+    fprintf(stderr, "[tc_gather] dst %dx%dx%dx%d src C=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d CB=%d ncblk=%d Ntile=%d stages=%d lps=%d dual=%d CBt=%d stats=%d/%d stage_bytes=%d a_box=%d tiles=%d grid=%d\n",
+            g.dT, g.dH, g.dW, g.dC, g.sC, g.kt * g.kh * g.kw, p.bw, p.bh, p.bt, p.nloads, p.nsub, p.CB, p.ncblk, p.Ntile, p.num_stages, p.lps, p.dual_mma, p.CBt, p.reg_stats * 10 + p.drain_rs, p.mma_stats,
             p.stage_bytes, p.a_box_bytes, p.num_tiles, plan.grid);
   if (nparts != nullptr) *nparts = plan.grid;
   return check_launch("tc_gather_gemm_kernel");
