@@ -90,7 +90,6 @@ struct TileIter {
 // hardware requires them (TMA completion, tcgen05.commit), and the TMA pipeline moves `lps` loads per stage so that
 // one wait / one expect_tx / one commit covers a whole tile's worth of operands where shared memory allows.
 constexpr int BAR_SREADY = 3;   // +buf : epilogue (arrive) -> store warp (sync): staged tile complete
-constexpr int BAR_SFREE = 5;    // +buf : store warp (arrive) -> epilogue (sync): staging buffer may be overwritten
 constexpr int BAR_TEMPTY = 7;   // +acc : epilogue (arrive) -> MMA warp (sync): TMEM accumulator drained
 constexpr int BAR_HANDOFF = TC_EPI + 32;
 
@@ -118,6 +117,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   auto sdone_bar = [&](int b) { return bars + 8u * (2 * S + 7 + b); };
   const uint32_t tmem_slot = bars + 8u * (2 * S + 11);
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.off_bars + 8 * (2 * S + 11));
+  const uint32_t sfree_cnt = bars + 8u * (2 * S + 12);   // count of tiles whose TMA store has read its staging buffer
   float* stats_sm = reinterpret_cast<float*>(sm + p.off_stats);
   float* scratch = reinterpret_cast<float*>(sm + p.off_scratch);
 
@@ -127,11 +127,10 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tma_prefetch_desc(&tmD);
     if (p.CBt) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     for (int i = 0; i < S; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(sready_bar(a), TC_EPI); mbar_init(sdone_bar(a), 1);
-    }
+    for (int a = 0; a < 4; ++a) mbar_init(tfull_bar(a), 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(sready_bar(a), TC_EPI); mbar_init(sdone_bar(a), 1); }
     mbar_init(wbar, 1);
+    st_release_shared(sfree_cnt, 0u);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -180,43 +179,51 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     int rstage0 = 0, rstage1 = 0;
     uint32_t rphase0 = 0, rphase1 = 0;
     int it = 0;
+    // loop invariants in registers: this single thread's instruction count per stage is on the critical path of the
+    // short-K layers (one 128-pixel tile lasts ~1000 cycles)
+    const int lps = p.lps, ncblk = p.ncblk, nsub = p.nsub, CB = p.CB, Ntile = p.Ntile, red_C = p.red_C;
+    const int tss = p.tap_sub_stride;
+    const bool resident = p.w_resident != 0, dual = p.dual_mma != 0, skip_loads = (p.dbg_skip & 2) != 0;
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes, slot_f = (uint32_t)p.slot_bytes;
+    const uint32_t slot_t = (uint32_t)(p.unit_mode ? p.slot_bytes_t : p.slot_bytes), b_sub_bytes = (uint32_t)p.b_sub_bytes;
+    const int sw = p.bw * p.mw, sh = p.bh * p.mh, st_ = p.bt * p.mt;
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti.next(), ++it) {
       const int n_idx = ti.n, b = ti.b;
-      const int w0 = ti.w * p.bw * p.mw, h0 = ti.h * p.bh * p.mh, t0 = ti.t * p.bt * p.mt;
-      const int r = p.dual_mma ? (it & 1) : 0;
+      const int w0 = ti.w * sw, h0 = ti.h * sh, t0 = ti.t * st_;
+      const int r = dual ? (it & 1) : 0;
       int stage = r ? rstage1 : rstage0;
       uint32_t phase = r ? rphase1 : rphase0;
       int l = 0, cb = 0;
-      for (int base = 0; base < TL; base += p.lps) {
-        const int cnt = min(p.lps, TL - base);
+      for (int left = TL; left > 0; left -= lps) {
+        const int cnt = left < lps ? left : lps;
         const int sidx = r * RN + stage;
         const long long c0 = dbg ? clock64() : 0;
         mbar_wait(empty_bar(sidx), phase ^ 1u);
         if (dbg) w_prod += clock64() - c0;
-        if (p.dbg_skip & 2) {
+        if (skip_loads) {
           mbar_arrive(full_bar(sidx));
         } else {
-          {   // bytes of this stage: cnt loads starting at block cb, of which the tail blocks are narrow
-            const int ntail = (cb + cnt) / p.ncblk;   // each wrap of the block index passes the last block once
-            mbar_expect_tx(full_bar(sidx), (uint32_t)(cnt - ntail) * tx + (uint32_t)ntail * tx_t);
-          }
-          uint32_t sa = sbase + (uint32_t)sidx * p.stage_bytes;
+          uint32_t sa = sbase + (uint32_t)sidx * stage_bytes;
+          uint32_t bytes = 0;
           for (int j = 0; j < cnt; ++j) {
             const bool tail = cb == tailcb;
-            tma_load_5d(tail ? &tmA2 : &tmA, full_bar(sidx), sa, cb * p.CB, w0 + p.off_w[l], h0 + p.off_h[l], t0 + p.off_t[l], b);
-            const uint32_t sz = (uint32_t)((tail && p.unit_mode) ? p.slot_bytes_t : p.slot_bytes);
-            if (!p.w_resident) {
-              for (int s = 0; s < p.nsub; ++s) {
-                const int tap = p.tap0[l] + s * p.tap_sub_stride;
-                tma_load_2d(&tmB, full_bar(sidx), sa + sz - (p.nsub - s) * p.b_sub_bytes,
-                            tap * p.red_C + cb * p.CB, n_idx * p.Ntile);
+            tma_load_5d(tail ? &tmA2 : &tmA, full_bar(sidx), sa, cb * CB, w0 + p.off_w[l], h0 + p.off_h[l], t0 + p.off_t[l], b);
+            const uint32_t sz = tail ? slot_t : slot_f;
+            bytes += tail ? tx_t : tx;
+            if (!resident) {
+              for (int s = 0; s < nsub; ++s) {
+                const int tap = p.tap0[l] + s * tss;
+                tma_load_2d(&tmB, full_bar(sidx), sa + sz - (uint32_t)(nsub - s) * b_sub_bytes, tap * red_C + cb * CB, n_idx * Ntile);
               }
             }
             sa += sz;
-            if (++cb == p.ncblk) { cb = 0; ++l; }
+            if (++cb == ncblk) { cb = 0; ++l; }
           }
+          // armed after the copies are issued: the phase cannot complete before this arrival, and the transaction count
+          // may run negative in between
+          mbar_expect_tx(full_bar(sidx), bytes);
         }
         if (++stage == RN) { stage = 0; phase ^= 1u; }
       }
@@ -240,7 +247,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t nsub_bsub = (uint32_t)p.nsub * ((uint32_t)p.b_sub_bytes >> 4);
     const uint32_t lo0 = smem_desc_lo(sbase, 16);
     const uint32_t wlo0 = smem_desc_lo(sbase + (uint32_t)p.off_wgt, 16);
-    const int ksteps_full = p.CB >> 4, ncblk = p.ncblk, nsub = p.nsub, lps = p.lps;
+    const int ksteps_full = p.CB >> 4, ksteps_last = p.ksteps_last, ncblk = p.ncblk, nsub = p.nsub, lps = p.lps;
+    const bool skip_rest = (p.dbg_skip & 4) != 0;
     const bool resident = p.w_resident != 0;
     const uint32_t b_step = resident ? (uint32_t)p.w_row_bytes >> 4 : b_sub;
     const uint32_t w_tap = (uint32_t)nsub * ((uint32_t)p.w_row_bytes >> 4);
@@ -274,7 +282,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     };
     if (resident) { mbar_wait(wbar, 0u); tc_fence_after(); }
     for (; it < my_tiles; it += tstep) {
-      const int acc = p.acc_bufs == 2 ? (it & 1) : 0;
+      const int acc = it & (p.acc_bufs - 1);   // 1, 2 or 4 accumulators
       long long c0 = dbg ? clock64() : 0;
       if (it >= p.acc_bufs) named_bar_sync(BAR_TEMPTY + acc, BAR_HANDOFF);   // epilogue drained this accumulator
       if (dbg) w_te += clock64() - c0;
@@ -294,25 +302,39 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           uint32_t a_slot = lo0 + (uint32_t)sidx * stage16;
           uint32_t w_l = w_lo;
           int c = cb;
-          uint32_t accum = accumulate;
+          bool first = accumulate == 0;
           for (int j = 0; j < cnt; ++j) {
             const bool tail = c == tailcb;
-            const int ksteps = (c == ncblk - 1) ? p.ksteps_last : ksteps_full;
+            const int ksteps = (c == ncblk - 1) ? ksteps_last : ksteps_full;
             const uint32_t sz = tail ? slot16_t : slot16;
             const uint32_t a_hi = tail ? hi_t : hi, a_step = tail ? a_sub_t : a_sub;
             const uint32_t b_hi = (tail && resident) ? hi_t : hi;   // streamed weights always arrive as full-width boxes
             uint32_t a_lo = a_slot;
             uint32_t b_lo = resident ? (w_l + (uint32_t)c * b_sub) : (a_slot + sz - nsub_bsub);
-            for (int s = 0; s < nsub; ++s) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k < ksteps && !((p.dbg_skip & 4) && (k > 0 || s > 0))) {
-                  umma_bf16_lh(tmem_d, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc, accum);
-                  accum = 1;
+            int s = 0;
+            if (first) {   // the tile's first MMA overwrites the accumulator
+              umma_bf16_lh(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, 0u);
+              first = false;
+              if (!skip_rest)
+                for (int k = 1; k < ksteps; ++k) umma_bf16_acc(tmem_d, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc);
+              a_lo += a_step; b_lo += b_step;
+              s = 1;
+            }
+            if (!skip_rest) {
+              if (ksteps == 4) {
+                for (; s < nsub; ++s) {
+                  umma_bf16_acc(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc);
+                  umma_bf16_acc(tmem_d, a_lo + 2u, a_hi, b_lo + 2u, b_hi, idesc);
+                  umma_bf16_acc(tmem_d, a_lo + 4u, a_hi, b_lo + 4u, b_hi, idesc);
+                  umma_bf16_acc(tmem_d, a_lo + 6u, a_hi, b_lo + 6u, b_hi, idesc);
+                  a_lo += a_step; b_lo += b_step;
+                }
+              } else {
+                for (; s < nsub; ++s) {
+                  for (int k = 0; k < ksteps; ++k) umma_bf16_acc(tmem_d, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc);
+                  a_lo += a_step; b_lo += b_step;
                 }
               }
-              a_lo += a_step;
-              b_lo += b_step;
             }
             a_slot += sz;
             if (++c == ncblk) { c = 0; w_l += w_tap; }
@@ -334,11 +356,12 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   } else if (warp == 3) {
     // ===================== TMA store warp: staged tile -> global, off the epilogue's critical path ==========
     const int nst = (p.Ntile + p.cw - 1) / p.cw;
+    const bool two_bufs = p.st_bufs == 2;
     int it = 0;
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, ti.next()) {
-      const int buf = it % p.st_bufs;
+      const int buf = two_bufs ? (it & 1) : 0;
       named_bar_sync(BAR_SREADY + buf, BAR_HANDOFF);
       if (lane == 0) {
         const uint32_t staging_s = sbase + (uint32_t)(p.off_staging + buf * p.st_buf_bytes);
@@ -346,13 +369,12 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tma_store_5d(&tmD, staging_s + (uint32_t)(ch * p.st_chunk_bytes), ti.n * p.Ntile + ch * p.cw, ti.w * p.bw,
                        ti.h * p.bh, ti.t * p.bt, ti.b);
         tma_store_commit();
-        if (p.st_bufs == 2) tma_store_wait_read1();   // the previous tile's store has finished reading its buffer
-        else tma_store_wait_read();
+        tma_store_wait_read();   // this tile's store has finished reading its staging buffer
+        // publish "tiles 0..it have left their staging buffers": the epilogue warps poll this counter (a ~30-cycle
+        // shared-memory load) instead of meeting at a barrier, so they never wait for each other or for this warp
+        st_release_shared(sfree_cnt, (uint32_t)(it + 1));
       }
       __syncwarp();
-      // release the buffer whose store has been read, if a later tile will use it
-      const int done_it = p.st_bufs == 2 ? it - 1 : it;
-      if (done_it >= 0 && done_it + p.st_bufs < my_tiles) named_bar_arrive(BAR_SFREE + (done_it % p.st_bufs), BAR_HANDOFF);
     }
     if (lane == 0) tma_store_wait_all();
   } else if (warp >= 4) {
@@ -367,6 +389,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t row_off = (uint32_t)(e * p.st_rowbytes);
     const uint32_t st_mask = (uint32_t)p.st_mask;
     const bool legacy_stats = p.has_stats && !p.mma_stats && !STATS;
+    const int st_bufs = p.st_bufs, bw_ = p.bw, bh_ = p.bh, bt_ = p.bt, dW_ = p.dW, dH_ = p.dH, dT_ = p.dT;
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
@@ -384,13 +407,13 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, ti.next()) {
       const int n_idx = ti.n, b = ti.b;
-      const int w = ti.w * p.bw + lw, h = ti.h * p.bh + lh, t = ti.t * p.bt + lt;
-      const bool valid = (w < p.dW) && (h < p.dH) && (t < p.dT);
+      const int w = ti.w * bw_ + lw, h = ti.h * bh_ + lh, t = ti.t * bt_ + lt;
+      const bool valid = (w < dW_) && (h < dH_) && (t < dT_);
       const __nv_bfloat16* arow = nullptr;
       if (!STATS && p.has_addend && valid)
         arow = addend + p.a_off + (int64_t)b * p.a_sb + (int64_t)t * p.a_st + (int64_t)h * p.a_sh + (int64_t)w * p.a_sw +
                n_idx * p.Ntile;
-      const int buf = it % p.st_bufs;
+      const int buf = st_bufs == 2 ? (it & 1) : 0;
       uint8_t* staging = sm + p.off_staging + buf * p.st_buf_bytes;
 
       const long long c0 = dbg ? clock64() : 0;
@@ -400,9 +423,10 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       tc_fence_after();
       // the staging buffer is free once the TMA store issued st_bufs tiles ago has read it and (statistics MMAs) the
       // MMAs over it have retired
-      if (it >= p.st_bufs) {
-        named_bar_sync(BAR_SFREE + buf, BAR_HANDOFF);
-        if (p.mma_stats) mbar_wait(sdone_bar(buf), (uint32_t)(((it / p.st_bufs) - 1) & 1));
+      if (it >= st_bufs) {
+        const uint32_t need = (uint32_t)(it - st_bufs + 1);
+        while (ld_acquire_shared(sfree_cnt) < need) {}
+        if (p.mma_stats) mbar_wait(sdone_bar(buf), (uint32_t)(((it / st_bufs) - 1) & 1));
       }
       if (dbg) { const long long c2 = clock64(); w_a += c2 - c1; c1 = c2; }
 
@@ -638,7 +662,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1;
+static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1;
 int tc_option(const char* name, int value, bool set) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_opt_halo;
@@ -654,6 +678,7 @@ int tc_option(const char* name, int value, bool set) {
   else if (!strcmp(name, "tc_reg_stats")) slot = &g_opt_reg_stats;
   else if (!strcmp(name, "tc_dual_mma")) slot = &g_opt_dual;
   else if (!strcmp(name, "tc_tail")) slot = &g_opt_tail;
+  else if (!strcmp(name, "tc_acc4")) slot = &g_opt_acc4;
   if (slot == nullptr) return -1;
   if (set) *slot = value;
   return *slot;
@@ -744,7 +769,9 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
   p.st_chunks = (p.Ntile + p.cw - 1) / p.cw;
   if (p.mma_stats && p.st_chunks < p.stat_M / p.cw) p.st_chunks = p.stat_M / p.cw;   // the Gram A operand spans stat_M channels
   p.st_buf_bytes = p.st_chunks * p.st_chunk_bytes;
-  p.acc_bufs = (p.mma_stats && 4 * p.Ntile > 512) ? 1 : 2;
+  // TMEM accumulators: the commit -> epilogue wake-up -> drain -> release -> next MMA round trip is ~1200 cycles, longer than a
+  // short-K tile, so narrow tiles keep four accumulators in flight
+  p.acc_bufs = (p.mma_stats && 4 * p.Ntile > 512) ? 1 : ((!p.mma_stats && g_opt_acc4 && 4 * p.Ntile <= 512) ? 4 : 2);
   const int wgt_total = used_taps * p.w_row_bytes;
   p.w_resident = (g_opt_resident && p.n_ntiles == 1 && wgt_total <= 98304) ? 1 : 0;
   const int stats_bytes = round_up(2 * g.dC * 4, 16);
@@ -856,7 +883,7 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
       if (st > 8) st = 8;
       if (st < 2) continue;
       const int groups = (total_loads + lps - 1) / lps;
-      const bool dual_ok = g_opt_dual && p.acc_bufs == 2 && !p.mma_stats && st / 2 >= groups;
+      const bool dual_ok = g_opt_dual && p.acc_bufs >= 2 && !p.mma_stats && st / 2 >= groups;
       const long score = (dual_ok ? 1000000L : 0L) + ((st >= 3 || dual_ok) ? 100000L : 0L) + 100L * lps + st;
       if (score > best_score) { best_score = score; best_lps = lps; best_stages = st; }
     }
@@ -892,7 +919,7 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
   p.tmem_cols = cols;
   // two MMA warps only when each private ring can hold a whole tile's stages (else the split rings lose prefetch depth)
   const int groups = (p.nloads * p.ncblk + p.lps - 1) / p.lps;
-  p.dual_mma = (g_opt_dual && p.acc_bufs == 2 && !p.mma_stats && p.num_stages / 2 >= groups) ? 1 : 0;
+  p.dual_mma = (g_opt_dual && p.acc_bufs >= 2 && !p.mma_stats && p.num_stages / 2 >= groups) ? 1 : 0;
   out->p = p;
   out->smem = (size_t)p.off_bars + 256 + 1024;
   const int sms = num_sms();

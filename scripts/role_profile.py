@@ -10,6 +10,8 @@ B = int(os.environ.get("B", "64"))
 lib = L.load(); L.require_device()
 dev = "cuda"
 dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+for kv in filter(None, os.environ.get("OPTS", "").split(",")):
+    k, v = kv.split("="); L.set_option(k, int(v))
 LAYERS = [
     ("stem.temporal 45->32", 45, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), (21, 64, 64)),
     ("conv2.spatial 32->72", 32, 72, (1, 3, 3), (1, 1, 1), (0, 1, 1), (21, 64, 64)),
