@@ -53,6 +53,7 @@ SIGNATURES = {
     "dp_conv_supported": (_i, [_pdesc, _i, _i]),
     "dp_conv_fwd": (_i, [_pdesc, _vp, _vp, _vp, _vp, _pint, _i, _vp]),
     "dp_conv_dgrad": (_i, [_pdesc, _vp, _vp, _vp, _vp, _i, _vp]),
+    "dp_conv_dgrad_bnstats": (_i, [_pdesc, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _pint, _i, _vp]),
     "dp_conv_wgrad_workspace": (_sz, [_pdesc, _i]),
     "dp_conv_wgrad": (_i, [_pdesc, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "dp_stem_supported": (_i, [_pdesc]),

@@ -106,6 +106,25 @@ DP_API int dp_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w_dg
   return simt_conv_dgrad(d, dy, w_dgrad, addend, dx, s);
 }
 
+DP_API int dp_conv_dgrad_bnstats(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx,
+                                 const void* y_prev, const float* scale_shift, float slope, float* part, int* nparts,
+                                 int impl, void* stream) {
+  int rc = validate(d);
+  if (rc != DP_OK) return rc;
+  DP_REQUIRE(dy && w_dgrad && dx && y_prev && scale_shift && part && nparts, DP_ERR_SHAPE, "dp_conv_dgrad_bnstats: NULL pointer");
+  const int r = resolve_impl(d, 1, impl);
+  DP_REQUIRE(r > 0, DP_ERR_UNSUPPORTED, "dp_conv_dgrad_bnstats: geometry not covered by the tcgen05 family");
+  cudaStream_t s = as_stream(stream);
+  if (r == DP_IMPL_TC && tc_dgrad_bnstats_supported(d))
+    return tc_conv_dgrad_bnstats(d, dy, w_dgrad, addend, dx, y_prev, scale_shift, slope, part, nparts, s);
+  rc = (r == DP_IMPL_TC) ? tc_conv_dgrad(d, dy, w_dgrad, addend, dx, s) : simt_conv_dgrad(d, dy, w_dgrad, addend, dx, s);
+  if (rc != DP_OK) return rc;
+  const int64_t rows = (int64_t)d->B * d->Ti * d->Hi * d->Wi;
+  // mean / rstd are not read by the reduction (the raw-y sums are centred in dp_bn_bwd_finalize)
+  return dp_bn_act_bwd_reduce(dx, y_prev, nullptr, scale_shift, scale_shift + d->Cp, scale_shift, scale_shift, slope, 1.f, part,
+                              nparts, rows, d->Cp, d->dtype, stream);
+}
+
 DP_API size_t dp_conv_wgrad_workspace(const dp_conv_desc* d, int impl) {
   if (validate(d) != DP_OK) return 0;
   size_t a = simt_wgrad_workspace(d);

@@ -26,6 +26,11 @@ int tc_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, fl
                 cudaStream_t s);
 int tc_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
                   cudaStream_t s);
+// dgrad whose epilogue also accumulates sum(g'), sum(g' * yprev) per channel of dx (BatchNorm backward of the producer)
+bool tc_dgrad_bnstats_supported(const dp_conv_desc* d);
+int tc_conv_dgrad_bnstats(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
+                          const void* yprev, const float* bn_scale_shift, float slope, float* part, int* nparts,
+                          cudaStream_t s);
 size_t tc_wgrad_workspace(const dp_conv_desc* d);
 int tc_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t s);

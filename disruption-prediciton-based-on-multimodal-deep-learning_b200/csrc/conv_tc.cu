@@ -56,6 +56,7 @@ struct TcParams {
   int off_staging, off_ones, off_stats, off_scratch, off_bars;
   int tmem_cols, layout_type, sbo_bytes;
   int has_stats, has_addend;
+  float slope;   // STATS == 2: LeakyReLU slope of the producing layer
   int dbg_skip;  // development: 1 = no epilogue data movement / stores, 2 = no TMA loads, 4 = one MMA per load
   long long a_off, a_sw, a_sh, a_st, a_sb;  // addend view: element offset / strides of (w,h,t,b) in the dst tensor
   signed char off_w[TC_MAX_LOADS], off_h[TC_MAX_LOADS], off_t[TC_MAX_LOADS];
@@ -93,14 +94,19 @@ constexpr int BAR_SREADY = 3;   // +buf : epilogue (arrive) -> store warp (sync)
 constexpr int BAR_TEMPTY = 7;   // +acc : epilogue (arrive) -> MMA warp (sync): TMEM accumulator drained
 constexpr int BAR_HANDOFF = TC_EPI + 32;
 
-// RS > 0: unrolled accumulator drain, <= RS chunks of 16 channels per epilogue warp; STATS: BN statistics accumulated in
-// registers from the fp32 accumulators (RS <= 3)
-template <int RS, bool STATS>
+// RS > 0: unrolled accumulator drain, <= RS chunks of 16 channels per epilogue warp.
+// STATS (RS <= 3), accumulated in epilogue registers from the fp32 accumulators:
+//   1: forward BatchNorm statistics  sum(y), sum(y^2)  of the tile being written;
+//   2: (data gradient) the sums the BatchNorm backward of the PRODUCING layer needs,  sum(g'), sum(g' * yp)  with
+//      g = this tile (+ addend), yp = that layer's raw conv output, g' = g * lrelu'(scale * yp + shift): the stand-alone
+//      reduction pass over (g, yp) disappears
+template <int RS, int STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmA2,
                       const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ TcParams p,
-                      const __nv_bfloat16* __restrict__ addend, float* __restrict__ part, long long* __restrict__ dbg) {
+                      const __nv_bfloat16* __restrict__ addend, float* __restrict__ part, long long* __restrict__ dbg,
+                      const __nv_bfloat16* __restrict__ yprev, const float* __restrict__ bn_ss) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -141,6 +147,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int e0 = threadIdx.x - (TC_THREADS - TC_EPI);
     if (p.has_stats && !p.mma_stats && !STATS)
       for (int i = e0; i < 2 * p.dC; i += TC_EPI) stats_sm[i] = 0.f;
+    if (STATS == 2)   // scale[dC], shift[dC] of the producing layer's BatchNorm
+      for (int i = e0; i < 2 * p.dC; i += TC_EPI) stats_sm[i] = bn_ss[i];
     if (p.mma_stats) {   // the all-ones A operand of the column-sum MMA (any canonical layout: every element is 1)
       uint32_t* ones = reinterpret_cast<uint32_t*>(sm + p.off_ones);
       for (int i = e0; i < 512; i += TC_EPI) ones[i] = 0x3F803F80u;
@@ -154,10 +162,15 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only below
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t col_g = (uint32_t)(p.acc_bufs * p.Ntile), col_s = col_g + (uint32_t)p.Ntile;
+  // register budget per role: the four control warps (one warpgroup) give registers to the eight epilogue warps, whose
+  // statistics accumulators (up to 96 floats) and row prefetch would otherwise spill at the 168 registers of 384 threads
+  // (setmaxnreg at the top of every role branch: 96 for warps 0-3, 200 for warps 4-11: 4*32*96 + 8*32*200 = 63488 <= the 384*168 registers the CTA is launched with -- an inc beyond the launch-time pool never returns)
   const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int TL = p.nloads * p.ncblk;   // loads per tile, moved `lps` per pipeline stage
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (lane == 0) {
     // ===================== TMA producer =====================
     long long w_prod = 0;
     const long long t_start = dbg ? clock64() : 0;
@@ -230,7 +243,9 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (r) { rstage1 = stage; rphase1 = phase; } else { rstage0 = stage; rphase0 = phase; }
     }
     if (dbg) { dbg[blockIdx.x * 8 + 0] = w_prod; dbg[blockIdx.x * 8 + 1] = clock64() - t_start; }
+    }
   } else if (warp == 1 || (warp == 2 && p.dual_mma)) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
     // dual mode: warps 1 and 2 take alternate tiles (each owns one TMEM accumulator), so one warp issues MMAs while
     // the other sits in the ~200-cycle mbarrier wait / tcgen05.commit latencies of its own tile
@@ -353,7 +368,10 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     if (p.mma_stats && it > 0) issue_stats(it - 1);
     if (dbg && lane == 0 && mw == 0) { dbg[blockIdx.x * 8 + 2] = w_full; dbg[blockIdx.x * 8 + 3] = w_te; dbg[blockIdx.x * 8 + 4] = clock64() - t_start; }
+  } else if (warp == 2) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");   // idle in single-issuer mode, but part of the warpgroup
   } else if (warp == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     // ===================== TMA store warp: staged tile -> global, off the epilogue's critical path ==========
     const int nst = (p.Ntile + p.cw - 1) / p.cw;
     const bool two_bufs = p.st_bufs == 2;
@@ -378,6 +396,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     if (lane == 0) tma_store_wait_all();
   } else if (warp >= 4) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     // ===================== epilogue: TMEM -> bf16 -> swizzled staging tile =====================
     const int et = threadIdx.x - (TC_THREADS - TC_EPI);  // 0..255
     const int q = warp & 3;                              // TMEM lane quadrant this warp may access
@@ -393,8 +412,9 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
+    long long* const edbg = STATS == 2 ? nullptr : dbg;   // no role counters in the register-starved BN-backward variant
     long long w_tf = 0, w_a = 0, w_b = 0, w_c = 0, w_d = 0;
-    const long long t_start = dbg ? clock64() : 0;
+    const long long t_start = edbg ? clock64() : 0;
     constexpr int NS = STATS ? RS : 1;
     float ssum[NS][16], ssq[NS][16];   // per-thread (one pixel row) channel sums over all tiles
     if (STATS) {
@@ -409,17 +429,34 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int n_idx = ti.n, b = ti.b;
       const int w = ti.w * bw_ + lw, h = ti.h * bh_ + lh, t = ti.t * bt_ + lt;
       const bool valid = (w < dW_) && (h < dH_) && (t < dT_);
-      const __nv_bfloat16* arow = nullptr;
-      if (!STATS && p.has_addend && valid)
-        arow = addend + p.a_off + (int64_t)b * p.a_sb + (int64_t)t * p.a_st + (int64_t)h * p.a_sh + (int64_t)w * p.a_sw +
-               n_idx * p.Ntile;
+      // element offset of this pixel's row in the destination tensor (addend and, STATS == 2, the producer's conv output)
+      int64_t roff = 0;
+      if (STATS != 1 && (p.has_addend || STATS == 2) && valid)
+        roff = p.a_off + (int64_t)b * p.a_sb + (int64_t)t * p.a_st + (int64_t)h * p.a_sh + (int64_t)w * p.a_sw + n_idx * p.Ntile;
+      const __nv_bfloat16* arow = (STATS != 1 && p.has_addend && valid) ? addend + roff : nullptr;
       const int buf = st_bufs == 2 ? (it & 1) : 0;
       uint8_t* staging = sm + p.off_staging + buf * p.st_buf_bytes;
+      // STATS == 2: this pixel's row of the producing layer's conv output, fetched before the accumulator wait
+      uint4 yq[STATS == 2 ? 2 * RS : 1];
+      if (STATS == 2) {
+        const int nch = (cend - cbeg) >> 4;
+        const __nv_bfloat16* yrow = yprev + roff + cbeg;
+#pragma unroll
+        for (int j = 0; j < (STATS == 2 ? RS : 0); ++j) {
+          if (j < nch && valid) {
+            yq[2 * j] = *reinterpret_cast<const uint4*>(yrow + 16 * j);
+            yq[2 * j + 1] = *reinterpret_cast<const uint4*>(yrow + 16 * j + 8);
+          } else {
+            yq[2 * j] = make_uint4(0, 0, 0, 0);
+            yq[2 * j + 1] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
 
-      const long long c0 = dbg ? clock64() : 0;
+      const long long c0 = edbg ? clock64() : 0;
       mbar_wait(tfull_bar(acc), acc_phase);
-      if (dbg) w_tf += clock64() - c0;
-      long long c1 = dbg ? clock64() : 0;
+      if (edbg) w_tf += clock64() - c0;
+      long long c1 = edbg ? clock64() : 0;
       tc_fence_after();
       // the staging buffer is free once the TMA store issued st_bufs tiles ago has read it and (statistics MMAs) the
       // MMAs over it have retired
@@ -428,7 +465,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         while (ld_acquire_shared(sfree_cnt) < need) {}
         if (p.mma_stats) mbar_wait(sdone_bar(buf), (uint32_t)(((it / st_bufs) - 1) & 1));
       }
-      if (dbg) { const long long c2 = clock64(); w_a += c2 - c1; c1 = c2; }
+      if (edbg) { const long long c2 = clock64(); w_a += c2 - c1; c1 = c2; }
 
       const uint32_t taddr = tmem_base + (uint32_t)(acc * p.Ntile) + ((uint32_t)(q * 32) << 16);
       auto store16 = [&](const float* f, int c) {   // 16 consecutive channels starting at channel c of this tile
@@ -465,32 +502,56 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (!(p.dbg_skip & 1)) {
           const int nch = (cend - cbeg) >> 4;
 #pragma unroll
-          for (int j0 = 0; j0 < (RS > 0 ? RS : 1); j0 += 2) {   // two chunks in flight per wait
-            uint32_t v[2][16];
+          // two chunks in flight per wait (one in the BN-backward mode, whose 96 accumulators + prefetched row leave no
+          // registers for a second: a spill in this loop costs far more than the extra TMEM round trip)
+          constexpr int STEP = STATS == 2 ? 1 : 2;
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
+          for (int j0 = 0; j0 < (RS > 0 ? RS : 1); j0 += STEP) {
+            uint32_t v[STEP][16];
+#pragma unroll
+            for (int jj = 0; jj < STEP; ++jj)
               if (j0 + jj < RS && j0 + jj < nch) tmem_ld16_nowait(taddr + (uint32_t)(cbeg + 16 * (j0 + jj)), v[jj]);
-            tmem_wait_ld16(v[0]); tmem_wait_ld16(v[1]);
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
+            for (int jj = 0; jj < STEP; ++jj) tmem_wait_ld16(v[jj]);
+#pragma unroll
+            for (int jj = 0; jj < STEP; ++jj) {
               if (j0 + jj < RS && j0 + jj < nch) {
                 float f[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) f[k] = valid ? __uint_as_float(v[jj][k]) : 0.f;
-                if (STATS) {
-                  constexpr int dummy = 0;
-                  const int js = (j0 + jj < NS) ? j0 + jj : dummy;
+                if (STATS != 1 && arow != nullptr) {
+                  const int c = cbeg + 16 * (j0 + jj);
+                  const f8 a0 = ld8(arow + c), a1 = ld8(arow + c + 8);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) { f[k] += a0.v[k]; f[8 + k] += a1.v[k]; }
+                }
+                if (STATS == 1) {
+                  const int js = (j0 + jj < NS) ? j0 + jj : 0;
 #pragma unroll
                   for (int k = 0; k < 16; ++k) {
                     ssum[js][k] += f[k];
                     ssq[js][k] = fmaf(f[k], f[k], ssq[js][k]);
                   }
                 }
-                if (!STATS && arow != nullptr) {
+                if (STATS == 2) {
+                  const int js = (j0 + jj < NS) ? j0 + jj : 0;
                   const int c = cbeg + 16 * (j0 + jj);
-                  const f8 a0 = ld8(arow + c), a1 = ld8(arow + c + 8);
+                  const __nv_bfloat162* y2 = reinterpret_cast<const __nv_bfloat162*>(&yq[STATS == 2 ? 2 * js : 0]);
 #pragma unroll
-                  for (int k = 0; k < 8; ++k) { f[k] += a0.v[k]; f[8 + k] += a1.v[k]; }
+                  for (int k = 0; k < 8; ++k) {
+                    const float2 yv = __bfloat1622float2(y2[k]);
+                    float g0 = f[2 * k], g1 = f[2 * k + 1];
+                    if (p.slope != 1.f) {
+                      const float u0 = fmaf(yv.x, stats_sm[c + 2 * k], stats_sm[p.dC + c + 2 * k]);
+                      const float u1 = fmaf(yv.y, stats_sm[c + 2 * k + 1], stats_sm[p.dC + c + 2 * k + 1]);
+                      g0 *= u0 > 0.f ? 1.f : p.slope;
+                      g1 *= u1 > 0.f ? 1.f : p.slope;
+                    }
+                    ssum[js][2 * k] += g0;
+                    ssum[js][2 * k + 1] += g1;
+                    ssq[js][2 * k] = fmaf(g0, yv.x, ssq[js][2 * k]);
+                    ssq[js][2 * k + 1] = fmaf(g1, yv.y, ssq[js][2 * k + 1]);
+                  }
                 }
                 store16(f, cbeg + 16 * (j0 + jj));
               }
@@ -512,7 +573,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (rem >= 64) emit16(vb + 16, c0c + 48);
         }
       }
-      if (dbg) { const long long c2 = clock64(); w_b += c2 - c1; c1 = c2; }
+      if (edbg) { const long long c2 = clock64(); w_b += c2 - c1; c1 = c2; }
       // accumulator drained: hand the TMEM buffer back to the MMA warp; publish the staged tile to the async proxy
       tc_fence_before();
       if (it + p.acc_bufs < my_tiles) named_bar_arrive(BAR_TEMPTY + acc, BAR_HANDOFF);
@@ -520,7 +581,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (legacy_stats) named_bar_sync(1, TC_EPI);
       named_bar_arrive(BAR_SREADY + buf, BAR_HANDOFF);   // the TMA-store warp may read the tile
       if (p.mma_stats) mbar_arrive(sready_bar(buf));     // ... and so may the statistics MMAs
-      if (dbg) { const long long c2 = clock64(); w_c += c2 - c1; c1 = c2; }
+      if (edbg) { const long long c2 = clock64(); w_c += c2 - c1; c1 = c2; }
       if (legacy_stats) {
         // fallback (N tiles > 1): per-channel sum / sum of squares of the bf16 tile from the (unswizzled) staging tile
         const int row_bytes = p.st_rowbytes;
@@ -564,12 +625,12 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // and the named barriers above order these readers before any thread can start the next drain into it
         named_bar_sync(2, TC_EPI);
       }
-      if (dbg) { const long long c2 = clock64(); w_d += c2 - c1; c1 = c2; }
+      if (edbg) { const long long c2 = clock64(); w_d += c2 - c1; c1 = c2; }
       if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1u; }
     }
-    if (dbg && et == 0) {
-      dbg[blockIdx.x * 8 + 5] = w_tf; dbg[blockIdx.x * 8 + 6] = clock64() - t_start;
-      long long* d2 = dbg + 148 * 8 + blockIdx.x * 8;
+    if (edbg && et == 0) {
+      edbg[blockIdx.x * 8 + 5] = w_tf; edbg[blockIdx.x * 8 + 6] = clock64() - t_start;
+      long long* d2 = edbg + 148 * 8 + blockIdx.x * 8;
       d2[0] = w_a; d2[1] = w_b; d2[2] = w_c; d2[3] = w_d;
     }
     if (STATS) {
@@ -662,7 +723,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1;
+static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64;
 int tc_option(const char* name, int value, bool set) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_opt_halo;
@@ -679,6 +740,7 @@ int tc_option(const char* name, int value, bool set) {
   else if (!strcmp(name, "tc_dual_mma")) slot = &g_opt_dual;
   else if (!strcmp(name, "tc_tail")) slot = &g_opt_tail;
   else if (!strcmp(name, "tc_acc4")) slot = &g_opt_acc4;
+  else if (!strcmp(name, "tc_bwd_stats_max")) slot = &g_opt_bwd_stats_max;
   if (slot == nullptr) return -1;
   if (set) *slot = value;
   return *slot;
@@ -712,7 +774,7 @@ struct TcPlan {
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
+static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, bool bwd_stats = false) {
   if (!g_opt_tc) return false;
   const int taps = g.kt * g.kh * g.kw;
   if (taps > TC_MAX_LOADS || taps < 1) return false;
@@ -751,7 +813,11 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out) {
   p.has_stats = has_stats ? 1 : 0;
   // statistics: in epilogue registers from the fp32 accumulators (<= 3 chunks of 16 channels per epilogue warp), else
   // on the tensor core (Gram + ones MMAs over the staged bf16 tile), else from the staged tile on the CUDA cores
-  p.reg_stats = (has_stats && g_opt_reg_stats && p.n_ntiles == 1 && p.Ntile <= 96) ? 1 : 0;
+  p.reg_stats = (has_stats && (g_opt_reg_stats || bwd_stats) && p.n_ntiles == 1 && p.Ntile <= 96) ? 1 : 0;
+  // the BN-backward sums exist only in the register mode, and only pay off up to 64 destination channels: each epilogue
+  // thread reads its own pixel row of the producer's output (one 32-byte sector per lane and load), which at 80 channels
+  // costs more LSU wavefronts than the stand-alone reduction pass saves (measured: 1229 us fused vs 310 + 350 us)
+  if (bwd_stats && (!p.reg_stats || p.Ntile > g_opt_bwd_stats_max)) return false;
   p.drain_rs = (!has_stats || p.reg_stats) ? ((p.Ntile >> 4) + 1) / 2 : 0;
   p.mma_stats = (has_stats && !p.reg_stats && g_opt_mma_stats && p.n_ntiles == 1 && p.Ntile <= 128) ? 1 : 0;
   const bool chunked = p.n_ntiles == 1 && (p.mma_stats || ((!has_stats || p.reg_stats) && g_opt_chunked));
@@ -981,13 +1047,16 @@ static int encode_wgt_map(CUtensorMap* m, const void* ptr, int Ktot, int rows, i
 }
 
 static int launch_gather(const GatherProblem& g, const void* src, const void* wgt, void* dst, const void* addend,
-                         float* part, int* nparts, cudaStream_t s) {
+                         float* part, int* nparts, cudaStream_t s, const void* yprev = nullptr, const float* bn_ss = nullptr,
+                         float slope = 1.f) {
   TcPlan plan;
-  DP_REQUIRE(plan_gather(g, part != nullptr, &plan), DP_ERR_UNSUPPORTED, "tcgen05 conv: geometry not supported");
+  const bool bwd_stats = yprev != nullptr;
+  DP_REQUIRE(plan_gather(g, part != nullptr, &plan, bwd_stats), DP_ERR_UNSUPPORTED, "tcgen05 conv: geometry not supported");
   DP_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)wgt & 15) == 0 && ((uintptr_t)dst & 15) == 0, DP_ERR_ALIGN,
              "tcgen05 conv: tensors must be 16-byte aligned");
   TcParams& p = plan.p;
   p.has_addend = addend != nullptr ? 1 : 0;
+  p.slope = slope;
   p.dbg_skip = g_opt_dbg_skip;
   const CUtensorMapSwizzle sw = p.CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                            : (p.CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -1020,23 +1089,26 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const __nv_bfloat16*, float*,
-                         long long*);
-  static KernFn const kerns[10] = {tc_gather_gemm_kernel<0, false>, tc_gather_gemm_kernel<1, true>, tc_gather_gemm_kernel<2, true>,
-                                   tc_gather_gemm_kernel<3, true>,  tc_gather_gemm_kernel<1, false>, tc_gather_gemm_kernel<2, false>,
-                                   tc_gather_gemm_kernel<3, false>, tc_gather_gemm_kernel<4, false>, tc_gather_gemm_kernel<5, false>,
-                                   tc_gather_gemm_kernel<8, false>};
+                         long long*, const __nv_bfloat16*, const float*);
+  static KernFn const kerns[13] = {tc_gather_gemm_kernel<0, 0>, tc_gather_gemm_kernel<1, 1>, tc_gather_gemm_kernel<2, 1>,
+                                   tc_gather_gemm_kernel<3, 1>, tc_gather_gemm_kernel<1, 0>, tc_gather_gemm_kernel<2, 0>,
+                                   tc_gather_gemm_kernel<3, 0>, tc_gather_gemm_kernel<4, 0>, tc_gather_gemm_kernel<5, 0>,
+                                   tc_gather_gemm_kernel<8, 0>, tc_gather_gemm_kernel<1, 2>, tc_gather_gemm_kernel<2, 2>,
+                                   tc_gather_gemm_kernel<3, 2>};
   std::call_once(attr_once, [] {
-    for (int i = 0; i < 10 && attr_err == cudaSuccess; ++i)
+    for (int i = 0; i < 13 && attr_err == cudaSuccess; ++i)
       attr_err = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
   });
   DP_REQUIRE(attr_err == cudaSuccess, DP_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s",
              cudaGetErrorString(attr_err));
   long long* dbg = (g_dbg && g_dbg_slots >= (size_t)148 * 16) ? g_dbg : nullptr;
   int ki = 0;
-  if (p.reg_stats) ki = p.drain_rs;                                   // 1..3
+  if (p.reg_stats && bwd_stats) ki = 9 + p.drain_rs;                  // 10..12
+  else if (p.reg_stats) ki = p.drain_rs;                              // 1..3
   else if (p.drain_rs >= 1 && p.drain_rs <= 5) ki = 3 + p.drain_rs;   // 4..8
   else if (p.drain_rs >= 6 && p.drain_rs <= 8) ki = 9;
-  launch_pdl(kerns[ki], dim3(plan.grid), dim3(TC_THREADS), plan.smem, s, tmA, tmB, tmD, tmA2, tmB2, p, (const __nv_bfloat16*)addend, part, dbg);
+  launch_pdl(kerns[ki], dim3(plan.grid), dim3(TC_THREADS), plan.smem, s, tmA, tmB, tmD, tmA2, tmB2, p, (const __nv_bfloat16*)addend, part, dbg,
+             (const __nv_bfloat16*)yprev, bn_ss);
   if (getenv("DP_DEBUG_PLAN"))
     fprintf(stderr, "[tc_gather] dst %dx%dx%dx%d src C=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d CB=%d ncblk=%d Ntile=%d stages=%d lps=%d dual=%d CBt=%d stats=%d/%d stage_bytes=%d a_box=%d tiles=%d grid=%d\n",
             g.dT, g.dH, g.dW, g.dC, g.sC, g.kt * g.kh * g.kw, p.bw, p.bh, p.bt, p.nloads, p.nsub, p.CB, p.ncblk, p.Ntile, p.num_stages, p.lps, p.dual_mma, p.CBt, p.reg_stats * 10 + p.drain_rs, p.mma_stats,
@@ -1127,6 +1199,26 @@ int tc_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, fl
 }
 
 bool tc_fwd_view_supported(const dp_conv_desc* d) { return tc_fwd_supported(d); }
+
+// stride-1 data gradient whose epilogue also produces the BatchNorm-backward sums of the layer that produced x
+bool tc_dgrad_bnstats_supported(const dp_conv_desc* d) {
+  if (d->dtype != DP_BF16 || d->st != 1 || d->sh != 1 || d->sw != 1) return false;
+  GatherProblem g;
+  int ntaps = 0;
+  if (!dgrad_class(d, 0, 0, 0, &g, &ntaps) || ntaps == 0) return false;
+  TcPlan plan;
+  return plan_gather(g, true, &plan, true);
+}
+
+int tc_conv_dgrad_bnstats(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
+                          const void* yprev, const float* bn_scale_shift, float slope, float* part, int* nparts,
+                          cudaStream_t s) {
+  GatherProblem g;
+  int ntaps = 0;
+  DP_REQUIRE(d->st == 1 && d->sh == 1 && d->sw == 1 && dgrad_class(d, 0, 0, 0, &g, &ntaps) && ntaps > 0, DP_ERR_UNSUPPORTED,
+             "tcgen05 dgrad+stats: stride-1 convolutions only");
+  return launch_gather(g, dy, w, dx, addend, part, nparts, s, yprev, bn_scale_shift, slope);
+}
 
 int tc_conv_fwd_view(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* w, void* y,
                      float* part, int* nparts, cudaStream_t s) {

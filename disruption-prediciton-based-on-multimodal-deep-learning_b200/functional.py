@@ -18,7 +18,7 @@ import torch
 
 from . import _lib as L
 
-_STATE = {"dtype": torch.bfloat16, "impl": L.IMPL_AUTO}
+_STATE = {"dtype": torch.bfloat16, "impl": L.IMPL_AUTO, "fuse_bn_reduce": True}
 
 
 def set_compute_mode(mode: str) -> None:
@@ -378,8 +378,13 @@ def layer_forward(x, weight, gamma, beta, running_mean, running_var, cfg: LayerC
 
 
 def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope_res: float, need_dx: bool,
-                   addend=None, want_dres: bool = False):
-    """Returns (dx, dw, dgamma, dbeta, dres)."""
+                   addend=None, want_dres: bool = False, pre_part=None, next_bn=None):
+    """Returns (dx, dw, dgamma, dbeta, dres).
+
+    `next_bn` = (y_prev, stats_prev, slope_prev, box) of the layer that produced this layer's input x: the data
+    gradient then also writes the BatchNorm-backward sums of that layer (dp_conv_dgrad_bnstats) into box[0] =
+    (part, nparts), which the caller hands to that layer's layer_backward as `pre_part` so its reduction pass is
+    skipped."""
     lib = L.load()
     st = L.stream_ptr()
     x, y, out, stats, wd, geom = saved
@@ -388,16 +393,19 @@ def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope
     dz = dz.contiguous()
     if dz.dtype != y.dtype or dz.shape != y.shape:
         raise L.DpError(f"grad {tuple(dz.shape)} {dz.dtype} does not match activation {tuple(y.shape)} {y.dtype}")
-    part = torch.empty((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=dev)
-    nparts = C.c_int(0)
     mean, rstd, scale, shift = (stats[i].data_ptr() for i in range(4))
     elems = geom.esize * geom.rows_out * d.K
-    t0 = _pb()
-    L.check(lib.dp_bn_act_bwd_reduce(dz.data_ptr(), y.data_ptr(), _p(out), scale, shift, mean, rstd, cfg.slope,
-                                     float(slope_res), part.data_ptr(), C.byref(nparts), geom.rows_out, d.Kp, d.dtype,
-                                     st), "dp_bn_act_bwd_reduce")
-    if t0 is not None:
-        _pe(t0, "bn_act_bwd_reduce", 0.0, elems * (3 if out is not None else 2))
+    if pre_part is not None and out is None:
+        part, nparts = pre_part          # written by the consumer's data-gradient epilogue
+    else:
+        part = torch.empty((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=dev)
+        nparts = C.c_int(0)
+        t0 = _pb()
+        L.check(lib.dp_bn_act_bwd_reduce(dz.data_ptr(), y.data_ptr(), _p(out), scale, shift, mean, rstd, cfg.slope,
+                                         float(slope_res), part.data_ptr(), C.byref(nparts), geom.rows_out, d.Kp, d.dtype,
+                                         st), "dp_bn_act_bwd_reduce")
+        if t0 is not None:
+            _pe(t0, "bn_act_bwd_reduce", 0.0, elems * (3 if out is not None else 2))
     dgamma = torch.empty(d.K, dtype=torch.float32, device=dev)
     dbeta = torch.empty(d.K, dtype=torch.float32, device=dev)
     coef = torch.empty((2, d.Kp), dtype=torch.float32, device=dev)
@@ -439,8 +447,17 @@ def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope
             if addend.shape != x.shape or addend.dtype != x.dtype:
                 raise L.DpError("dgrad addend does not match the input activation")
         t0 = _pb()
-        L.check(lib.dp_conv_dgrad(C.byref(d), dy.data_ptr(), wd.data_ptr(), _p(addend), dx.data_ptr(), impl, st),
-                "dp_conv_dgrad")
+        if next_bn is not None:
+            y_prev, stats_prev, slope_prev, box = next_bn
+            npart = torch.empty((L.DP_MAX_PARTS, 2, d.Cp), dtype=torch.float32, device=dev)
+            nn_ = C.c_int(0)
+            L.check(lib.dp_conv_dgrad_bnstats(C.byref(d), dy.data_ptr(), wd.data_ptr(), _p(addend), dx.data_ptr(),
+                                              y_prev.data_ptr(), stats_prev[2].data_ptr(), float(slope_prev),
+                                              npart.data_ptr(), C.byref(nn_), impl, st), "dp_conv_dgrad_bnstats")
+            box.append((npart, nn_))
+        else:
+            L.check(lib.dp_conv_dgrad(C.byref(d), dy.data_ptr(), wd.data_ptr(), _p(addend), dx.data_ptr(), impl, st),
+                    "dp_conv_dgrad")
         if t0 is not None:
             _pe(t0, geom.families(impl)[2], geom.flops, io_bytes)
     elif addend is not None:
@@ -686,28 +703,38 @@ class ResBlockFn(torch.autograd.Function):
         # call order in forward: 0 c1.s, 1 c1.t, 2 c2.s, [3 ds.s, 4 ds.t], last = c2.t
         last = len(ctx.metas) - 1
 
-        def bwd(slot, dz, need_dx=True, addend=None, with_out=False, want_dres=False):
+        fuse = _STATE.get("fuse_bn_reduce", True) and out.dtype == torch.bfloat16
+
+        def bwd(slot, dz, need_dx=True, addend=None, with_out=False, want_dres=False, pre=None, nxt=None):
             xs, y, stats, wd = sv[slot]
             geom, cfg, wshape = ctx.metas[slot]
-            return layer_backward((xs, y, out if with_out else None, stats, wd, geom), dz, wshape, cfg, ctx.training,
-                                  ctx.slope_res, need_dx, addend=addend, want_dres=want_dres)
+            box = []
+            next_bn = None
+            if nxt is not None and fuse and need_dx:
+                _, y_n, stats_n, _ = sv[nxt]
+                next_bn = (y_n, stats_n, ctx.metas[nxt][1].slope, box)
+            res = layer_backward((xs, y, out if with_out else None, stats, wd, geom), dz, wshape, cfg, ctx.training,
+                                 ctx.slope_res, need_dx, addend=addend, want_dres=want_dres, pre_part=pre, next_bn=next_bn)
+            return res + (box[0] if box else None,)
 
+        # the data gradient of layer i+1 also produces the BatchNorm-backward sums of layer i (inside the block the
+        # producer of every conv input is known): c2.t -> c2.s -> c1.t -> c1.s
         grads = {}
-        d, dw, dg, db, dres = bwd(last, dout, with_out=True, want_dres=True)
+        d, dw, dg, db, dres, pp = bwd(last, dout, with_out=True, want_dres=True, nxt=2)
         grads[3] = (dw, dg, db)
-        d, dw, dg, db, _ = bwd(2, d)
+        d, dw, dg, db, _, pp = bwd(2, d, pre=pp, nxt=1)
         grads[2] = (dw, dg, db)
-        d, dw, dg, db, _ = bwd(1, d)
+        d, dw, dg, db, _, pp = bwd(1, d, pre=pp, nxt=0)
         grads[1] = (dw, dg, db)
         need_dx = ctx.needs_input_grad[0]
         if ctx.downsample:
-            ds, dw, dg, db, _ = bwd(4, dres)
+            ds, dw, dg, db, _, pq = bwd(4, dres, nxt=3)
             grads[5] = (dw, dg, db)
-            ds, dw, dg, db, _ = bwd(3, ds, need_dx=need_dx)
+            ds, dw, dg, db, _, _ = bwd(3, ds, need_dx=need_dx, pre=pq)
             grads[4] = (dw, dg, db)
-            dx, dw, dg, db, _ = bwd(0, d, need_dx=need_dx, addend=ds)
+            dx, dw, dg, db, _, _ = bwd(0, d, need_dx=need_dx, addend=ds, pre=pp)
         else:
-            dx, dw, dg, db, _ = bwd(0, d, need_dx=need_dx, addend=dres)
+            dx, dw, dg, db, _, _ = bwd(0, d, need_dx=need_dx, addend=dres, pre=pp)
         grads[0] = (dw, dg, db)
         flat = []
         for i in range(len(ctx.metas)):

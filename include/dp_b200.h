@@ -102,6 +102,15 @@ int dp_conv_fwd(const dp_conv_desc* d, const void* x, const void* w_fwd, void* y
 /* dx = conv_transpose(dy, w) (+ addend if non-NULL, same shape as dx). */
 int dp_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend,
                   void* dx, int impl, void* stream);
+/* dp_conv_dgrad plus the two per-channel sums the BatchNorm backward of the layer that PRODUCED x needs (the
+ * autograd of Conv3dBlock, R2Plus1D.py:44-54): with g = dx, yp = that layer's raw conv output (same shape as dx),
+ * g' = g * lrelu'(scale*yp + shift):  part[nparts][2][Cp] = (sum g', sum g'*yp) -- the same partials
+ * dp_bn_act_bwd_reduce(dx, yp, NULL, ...) writes.  On stride-1 geometries the tcgen05 kernel accumulates them in its
+ * epilogue (no pass over dx / yp); otherwise the data gradient is followed by that reduction.
+ * scale_shift = scale[Cp] followed by shift[Cp]. */
+int dp_conv_dgrad_bnstats(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend,
+                          void* dx, const void* y_prev, const float* scale_shift, float slope,
+                          float* part, int* nparts, int impl, void* stream);
 size_t dp_conv_wgrad_workspace(const dp_conv_desc* d, int impl);
 /* dw (fp32, (K,C,kt,kh,kw)) = x^T * dy, deterministic split reduction through `workspace`. */
 int dp_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw,

@@ -405,3 +405,65 @@ def test_fused_clip_adamw_matches_torch():
         assert rel_err(oa.last_grad_norm[0], norm_b) < 1e-5
         for pa, pb in zip(ps_a, ps_b):
             assert rel_err(pa.detach(), pb.detach()) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", [(72, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), 9, 16, 16),
+                                  (32, 72, (1, 3, 3), (1, 1, 1), (0, 1, 1), 5, 16, 16),
+                                  (45, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), 6, 16, 16),
+                                  (64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), 4, 8, 8),
+                                  (32, 115, (1, 3, 3), (1, 2, 2), (0, 1, 1), 4, 16, 16)],
+                         ids=lambda g: f"{g[0]}to{g[1]}_k{g[2]}_s{g[3]}")
+@pytest.mark.parametrize("slope", [1.0, 0.01])
+@pytest.mark.parametrize("use_add", [False, True])
+def test_dgrad_bnstats(geom, slope, use_add):
+    """dp_conv_dgrad_bnstats == dp_conv_dgrad followed by the BN-backward reduction of the producing layer
+    (fused in the tcgen05 epilogue on stride-1 geometries, composed otherwise)."""
+    lib = L.load()
+    B = 3
+    x, w = make_case(geom, B, torch.bfloat16, 5)
+    ref = torch_ref(geom, x, w)
+    dy = torch.randn_like(ref["y"], dtype=torch.float32).bfloat16().float()
+    Cc, K, k, s, p, T, H, W = geom
+    xi = to_int(x, torch.bfloat16)
+    gm = Fn.conv_geom(Cc, K, k, s, p, xi)
+    d = gm.desc
+    wf, wd = Fn.pack_weights(w.contiguous(), gm, torch.bfloat16, None)
+    dyi = to_int(dy, torch.bfloat16)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    yprev = torch.randn(xi.shape, generator=g).to(DEV).bfloat16()
+    yprev[..., Cc:] = 0
+    add = None
+    if use_add:
+        add = torch.randn(xi.shape, generator=g).to(DEV).bfloat16()
+        add[..., Cc:] = 0
+    ss = torch.zeros((2, d.Cp), dtype=torch.float32, device=DEV)
+    ss[0, :Cc] = torch.rand(Cc, generator=g).to(DEV) + 0.5
+    ss[1, :Cc] = torch.randn(Cc, generator=g).to(DEV) * 0.3
+    dx = torch.full(xi.shape, float("nan"), dtype=torch.bfloat16, device=DEV)
+    part = torch.zeros((L.DP_MAX_PARTS, 2, d.Cp), dtype=torch.float32, device=DEV)
+    nparts = C.c_int(0)
+    L.check(lib.dp_conv_dgrad_bnstats(C.byref(d), dyi.data_ptr(), wd.data_ptr(), None if add is None else add.data_ptr(),
+                                      dx.data_ptr(), yprev.data_ptr(), ss.data_ptr(), slope, part.data_ptr(),
+                                      C.byref(nparts), L.IMPL_AUTO, L.stream_ptr()), "dgrad_bnstats")
+    dx2 = torch.empty_like(dx)
+    L.check(lib.dp_conv_dgrad(C.byref(d), dyi.data_ptr(), wd.data_ptr(), None if add is None else add.data_ptr(),
+                              dx2.data_ptr(), L.IMPL_AUTO, L.stream_ptr()), "dgrad")
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx2), "the fused epilogue must not change the data gradient"
+    st = part[:nparts.value].double().sum(0)
+    # fp64 reference on the exact (unrounded) gradient: conv_transpose of the bf16 operands (+ addend)
+    gref = torch_ref(geom, x, w, dy)["dx"].double()
+    gi = gref.permute(0, 2, 3, 4, 1)
+    if add is not None:
+        gi = gi + add[..., :Cc].double()
+    yp = yprev[..., :Cc].double()
+    u = yp * ss[0, :Cc].double() + ss[1, :Cc].double()
+    gp = gi * torch.where(u > 0, 1.0, slope)
+    s0, s1 = gp.sum(dim=(0, 1, 2, 3)), (gp * yp).sum(dim=(0, 1, 2, 3))
+    scale0 = gp.abs().sum(dim=(0, 1, 2, 3)).max()
+    scale1 = (gp * yp).abs().sum(dim=(0, 1, 2, 3)).max()
+    e0 = float((st[0, :Cc] - s0).abs().max() / scale0)
+    e1 = float((st[1, :Cc] - s1).abs().max() / scale1)
+    assert e0 < 2e-3 and e1 < 2e-3, (e0, e1)
+    assert float(st[:, Cc:].abs().max()) == 0.0 if d.Cp > Cc else True
