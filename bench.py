@@ -89,6 +89,7 @@ class ClockSampler:
         self.idx = gpu_index
         self.rows = []
         self.proc = None
+        self.first = 0
 
     def start(self):
         try:
@@ -103,13 +104,20 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """Samples before this point (process start-up, warm-up) are not reported."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows[self.first:]
+        if len(rows) < 2:          # a timed region shorter than two sampling periods: include the warm-up steps (same work)
+            rows = self.rows[max(0, self.first - 5):]
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -273,6 +281,10 @@ def run_ours(args):
         return float(t.item())
 
     with dp_b200.compute_mode("bf16", args.conv_impl):
+        # nvidia-smi takes a few hundred ms to produce its first sample: start it before the warm-up, report from mark()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
         # ---- warm-up (eager), then capture the whole step into one CUDA graph and warm that up too ----
         for i in range(max(3, args.warmup)):
             loss = step(x_dev[i % n_host], y_dev)
@@ -292,9 +304,7 @@ def run_ours(args):
             assert torch.isfinite(loss).item(), "non-finite loss after graph capture"
 
         # ---- timed region A: inputs resident in HBM ----
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
+        sampler.mark()
         l0 = lib.dp_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -305,7 +315,6 @@ def run_ours(args):
         barrier()
         ms_dev = max_over_ranks(e0.elapsed_time(e1))
         launches = int(lib.dp_launch_count() - l0) if graphed is None else graphed.launches_per_step * args.steps
-        clocks = sampler.stop() if rank == 0 else None
         final_loss = float(loss.item())
 
         # ---- timed region B: end to end from pinned host memory (double-buffered H2D on a copy stream) ----
@@ -343,6 +352,7 @@ def run_ours(args):
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions
         h2d = host[0].numel() * 4 + ysrc.numel() * 8
         d2h = 4
 
