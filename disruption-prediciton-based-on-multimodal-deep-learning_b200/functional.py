@@ -18,7 +18,33 @@ import torch
 
 from . import _lib as L
 
-_STATE = {"dtype": torch.bfloat16, "impl": L.IMPL_AUTO, "fuse_bn_reduce": True}
+import os as _os
+
+_STATE = {"dtype": torch.bfloat16, "impl": L.IMPL_AUTO, "fuse_bn_reduce": True,
+          # weight gradients on a second stream: wgrad (tensor / shared-memory bound, one 256-thread CTA per SM) then
+          # overlaps the HBM-bound BatchNorm passes and the data gradient of the layers below it
+          "wgrad_stream": _os.environ.get("DP_WGRAD_STREAM", "0") == "1"}
+_SIDE = {}
+_PENDING = []   # (done event, tensors kept alive until the main stream has waited for it)
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    s = _SIDE.get(device.index)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _SIDE[device.index] = s
+    return s
+
+
+def join_side_stream() -> None:
+    """Make the current stream wait for every weight gradient still running on the side stream."""
+    if not _PENDING:
+        return
+    cur = torch.cuda.current_stream()
+    for done, _keep in _PENDING:
+        cur.wait_event(done)
+    _PENDING.clear()
+
 
 
 def set_compute_mode(mode: str) -> None:
@@ -428,17 +454,29 @@ def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope
                             else lib.dp_conv_wgrad_workspace(C.byref(d), impl))
     ws = _workspace(geom.ws_bytes, dev)
     io_bytes = geom.esize * (geom.rows_in * d.C + geom.rows_out * d.K)
-    t0 = _pb()
-    if geom.stem:
-        if need_dx:
-            raise L.DpError("the stem fast path has no data gradient")
-        L.check(lib.dp_stem_conv_wgrad(C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
-                                       st), "dp_stem_conv_wgrad")
+    side = _side_stream(dev) if (_STATE["wgrad_stream"] and PROFILER is None) else None
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream())      # dy (and x) are complete on the main stream
+        wctx = torch.cuda.stream(side)
     else:
-        L.check(lib.dp_conv_wgrad(C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
-                                  impl, st), "dp_conv_wgrad")
-    if t0 is not None:
-        _pe(t0, geom.families(impl)[3], geom.flops, io_bytes)
+        wctx = contextlib.nullcontext()
+    with wctx:
+        stw = L.stream_ptr()
+        t0 = _pb()
+        if geom.stem:
+            if need_dx:
+                raise L.DpError("the stem fast path has no data gradient")
+            L.check(lib.dp_stem_conv_wgrad(C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           stw), "dp_stem_conv_wgrad")
+        else:
+            L.check(lib.dp_conv_wgrad(C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(),
+                                      impl, stw), "dp_conv_wgrad")
+        if t0 is not None:
+            _pe(t0, geom.families(impl)[3], geom.flops, io_bytes)
+        if side is not None:
+            done = torch.cuda.Event()
+            done.record(side)
+            _PENDING.append((done, (x, dy, dw, ws)))
     dx = None
     if need_dx:
         dx = torch.empty_like(x)
@@ -489,6 +527,7 @@ class ConvBnActFn(torch.autograd.Function):
         xs, y, stats, wd = ctx.saved_tensors
         dx, dw, dg, db, _ = layer_backward((xs, y, None, stats, wd, ctx.geom), dz, ctx.wshape, ctx.cfg, ctx.training,
                                            1.0, ctx.needs_input_grad[0])
+        join_side_stream()
         return dx, dw, dg, db, None
 
 
@@ -517,6 +556,7 @@ class ConvBnActResFn(torch.autograd.Function):
         xs, y, out, stats, wd = ctx.saved_tensors
         dx, dw, dg, db, dres = layer_backward((xs, y, out, stats, wd, ctx.geom), dz, ctx.wshape, ctx.cfg, ctx.training,
                                               ctx.slope_res, ctx.needs_input_grad[0], want_dres=True)
+        join_side_stream()
         return dx, dw, dg, db, dres, None, None
 
 
@@ -542,6 +582,7 @@ class ConvFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, wd = ctx.saved_tensors
         lib = L.load()
+        join_side_stream()   # this wgrad shares the split workspace with the ones on the side stream
         geom, d, st, impl = ctx.geom, ctx.geom.desc, L.stream_ptr(), _STATE["impl"]
         dy = dy.contiguous()
         dw = torch.empty(ctx.wshape, dtype=torch.float32, device=x.device)
@@ -616,6 +657,7 @@ class StemConvBnActFn(torch.autograd.Function):
         xp, y, stats = ctx.saved_tensors
         _, dw, dg, db, _ = layer_backward((xp, y, None, stats, None, ctx.geom), dz, ctx.wshape, ctx.cfg, ctx.training,
                                           1.0, False)
+        join_side_stream()
         return None, dw, dg, db, None, None
 
 
@@ -739,6 +781,7 @@ class ResBlockFn(torch.autograd.Function):
         flat = []
         for i in range(len(ctx.metas)):
             flat.extend(grads[i])
+        join_side_stream()
         return (dx, None, *flat)
 
 
