@@ -47,6 +47,7 @@ struct TcParams {
   int b_box_bytes_t, b_sub_bytes_t, w_row_bytes;   // resident weights: compact tail block; bytes of one (load, sub-tap) row
   int reg_stats;            // BN statistics accumulated in epilogue registers
   int dual_mma;             // two MMA-issuing warps on alternate tiles
+  int MT;                   // 128-pixel sub-tiles per tile (1 or 2): one handshake round covers 128 * MT pixels
   int drain_rs;             // unrolled drain: chunks of 16 channels per epilogue warp (0 = generic loop)
   int w_resident, off_wgt;  // all weight blocks loaded once per CTA instead of once per stage
   int mma_stats, stat_M, acc_bufs;  // BN statistics accumulated in TMEM by the tensor core
@@ -100,7 +101,7 @@ constexpr int BAR_HANDOFF = TC_EPI + 32;
 //   2: (data gradient) the sums the BatchNorm backward of the PRODUCING layer needs,  sum(g'), sum(g' * yp)  with
 //      g = this tile (+ addend), yp = that layer's raw conv output, g' = g * lrelu'(scale * yp + shift): the stand-alone
 //      reduction pass over (g, yp) disappears
-template <int RS, int STATS>
+template <int RS, int STATS, int MT>   // MT: 128-row sub-tiles per tile (compile-time: the 128-pixel kernels pay nothing for it)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmA2,
@@ -164,12 +165,12 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const uint32_t col_g = (uint32_t)(p.acc_bufs * p.Ntile), col_s = col_g + (uint32_t)p.Ntile;
   // register budget per role: the four control warps (one warpgroup) give registers to the eight epilogue warps, whose
   // statistics accumulators (up to 96 floats) and row prefetch would otherwise spill at the 168 registers of 384 threads
-  // (setmaxnreg at the top of every role branch: 96 for warps 0-3, 200 for warps 4-11: 4*32*96 + 8*32*200 = 63488 <= the 384*168 registers the CTA is launched with -- an inc beyond the launch-time pool never returns)
+  // (BN-backward variants only -- the tighter budget measurably slows the control warps' issue loops -- setmaxnreg at the top of every role branch: 96 for warps 0-3, 200 for warps 4-11: 4*32*96 + 8*32*200 = 63488 <= the 384*168 registers the CTA is launched with -- an inc beyond the launch-time pool never returns)
   const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int TL = p.nloads * p.ncblk;   // loads per tile, moved `lps` per pipeline stage
 
   if (warp == 0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (STATS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     if (lane == 0) {
     // ===================== TMA producer =====================
     long long w_prod = 0;
@@ -245,7 +246,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (dbg) { dbg[blockIdx.x * 8 + 0] = w_prod; dbg[blockIdx.x * 8 + 1] = clock64() - t_start; }
     }
   } else if (warp == 1 || (warp == 2 && p.dual_mma)) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (STATS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
     // dual mode: warps 1 and 2 take alternate tiles (each owns one TMEM accumulator), so one warp issues MMAs while
     // the other sits in the ~200-cycle mbarrier wait / tcgen05.commit latencies of its own tile
@@ -260,6 +261,10 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t a_sub_t = (uint32_t)p.sub_row_bytes_t >> 4;
     const uint32_t slot16_t = (uint32_t)(p.unit_mode ? p.slot_bytes_t : p.slot_bytes) >> 4;
     const uint32_t nsub_bsub = (uint32_t)p.nsub * ((uint32_t)p.b_sub_bytes >> 4);
+    // second 128-row sub-tile of a 256-pixel tile: rows 128.. of the same box, accumulator columns Ntile..
+    constexpr bool two = MT == 2;
+    const uint32_t a_m1 = (uint32_t)(128 * p.CB * 2) >> 4, a_m1_t = (uint32_t)(128 * p.CBt * 2) >> 4;
+    const uint32_t d_m1 = (uint32_t)p.Ntile;
     const uint32_t lo0 = smem_desc_lo(sbase, 16);
     const uint32_t wlo0 = smem_desc_lo(sbase + (uint32_t)p.off_wgt, 16);
     const int ksteps_full = p.CB >> 4, ksteps_last = p.ksteps_last, ncblk = p.ncblk, nsub = p.nsub, lps = p.lps;
@@ -302,7 +307,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (it >= p.acc_bufs) named_bar_sync(BAR_TEMPTY + acc, BAR_HANDOFF);   // epilogue drained this accumulator
       if (dbg) w_te += clock64() - c0;
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Ntile);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * MT * p.Ntile);
       uint32_t accumulate = 0;
       uint32_t w_lo = wlo0;
       int cb = 0;
@@ -326,17 +331,22 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const uint32_t b_hi = (tail && resident) ? hi_t : hi;   // streamed weights always arrive as full-width boxes
             uint32_t a_lo = a_slot;
             uint32_t b_lo = resident ? (w_l + (uint32_t)c * b_sub) : (a_slot + sz - nsub_bsub);
+            const uint32_t a_m = tail ? a_m1_t : a_m1;
             int s = 0;
             if (first) {   // the tile's first MMA overwrites the accumulator
               umma_bf16_lh(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, 0u);
+              if (two) umma_bf16_lh(tmem_d + d_m1, a_lo + a_m, a_hi, b_lo, b_hi, idesc, 0u);
               first = false;
               if (!skip_rest)
-                for (int k = 1; k < ksteps; ++k) umma_bf16_acc(tmem_d, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc);
+                for (int k = 1; k < ksteps; ++k) {
+                  umma_bf16_acc(tmem_d, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc);
+                  if (two) umma_bf16_acc(tmem_d + d_m1, a_lo + a_m + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc);
+                }
               a_lo += a_step; b_lo += b_step;
               s = 1;
             }
             if (!skip_rest) {
-              if (ksteps == 4) {
+              if (ksteps == 4 && !two) {
                 for (; s < nsub; ++s) {
                   umma_bf16_acc(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc);
                   umma_bf16_acc(tmem_d, a_lo + 2u, a_hi, b_lo + 2u, b_hi, idesc);
@@ -344,9 +354,17 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                   umma_bf16_acc(tmem_d, a_lo + 6u, a_hi, b_lo + 6u, b_hi, idesc);
                   a_lo += a_step; b_lo += b_step;
                 }
-              } else {
+              } else if (!two) {
                 for (; s < nsub; ++s) {
                   for (int k = 0; k < ksteps; ++k) umma_bf16_acc(tmem_d, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc);
+                  a_lo += a_step; b_lo += b_step;
+                }
+              } else {
+                for (; s < nsub; ++s) {
+                  for (int k = 0; k < ksteps; ++k) {
+                    umma_bf16_acc(tmem_d, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc);
+                    umma_bf16_acc(tmem_d + d_m1, a_lo + a_m + 2u * k, a_hi, b_lo + 2u * k, b_hi, idesc);
+                  }
                   a_lo += a_step; b_lo += b_step;
                 }
               }
@@ -369,9 +387,9 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (p.mma_stats && it > 0) issue_stats(it - 1);
     if (dbg && lane == 0 && mw == 0) { dbg[blockIdx.x * 8 + 2] = w_full; dbg[blockIdx.x * 8 + 3] = w_te; dbg[blockIdx.x * 8 + 4] = clock64() - t_start; }
   } else if (warp == 2) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");   // idle in single-issuer mode, but part of the warpgroup
+    if (STATS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");   // idle in single-issuer mode, but part of the warpgroup
   } else if (warp == 3) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (STATS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     // ===================== TMA store warp: staged tile -> global, off the epilogue's critical path ==========
     const int nst = (p.Ntile + p.cw - 1) / p.cw;
     const bool two_bufs = p.st_bufs == 2;
@@ -396,7 +414,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     if (lane == 0) tma_store_wait_all();
   } else if (warp >= 4) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    if (STATS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     // ===================== epilogue: TMEM -> bf16 -> swizzled staging tile =====================
     const int et = threadIdx.x - (TC_THREADS - TC_EPI);  // 0..255
     const int q = warp & 3;                              // TMEM lane quadrant this warp may access
@@ -404,8 +422,12 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int chalf = (warp - 4) >> 2;                   // which half of the columns this warp drains
     const int csplit = ((p.Ntile >> 4) + 1) / 2 * 16;    // columns [0,csplit) -> half 0, [csplit,Ntile) -> half 1
     const int cbeg = chalf ? csplit : 0, cend = chalf ? p.Ntile : csplit;
-    const int lw = e % p.bw, lh = (e / p.bw) % p.bh, lt = e / (p.bw * p.bh);
-    const uint32_t row_off = (uint32_t)(e * p.st_rowbytes);
+    int lw[MT], lh[MT], lt[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const int em = e + 128 * m;
+      lw[m] = em % p.bw; lh[m] = (em / p.bw) % p.bh; lt[m] = em / (p.bw * p.bh);
+    }
     const uint32_t st_mask = (uint32_t)p.st_mask;
     const bool legacy_stats = p.has_stats && !p.mma_stats && !STATS;
     const int st_bufs = p.st_bufs, bw_ = p.bw, bh_ = p.bh, bt_ = p.bt, dW_ = p.dW, dH_ = p.dH, dT_ = p.dT;
@@ -427,23 +449,28 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, ti.next()) {
       const int n_idx = ti.n, b = ti.b;
-      const int w = ti.w * bw_ + lw, h = ti.h * bh_ + lh, t = ti.t * bt_ + lt;
-      const bool valid = (w < dW_) && (h < dH_) && (t < dT_);
-      // element offset of this pixel's row in the destination tensor (addend and, STATS == 2, the producer's conv output)
-      int64_t roff = 0;
-      if (STATS != 1 && (p.has_addend || STATS == 2) && valid)
-        roff = p.a_off + (int64_t)b * p.a_sb + (int64_t)t * p.a_st + (int64_t)h * p.a_sh + (int64_t)w * p.a_sw + n_idx * p.Ntile;
-      const __nv_bfloat16* arow = (STATS != 1 && p.has_addend && valid) ? addend + roff : nullptr;
       const int buf = st_bufs == 2 ? (it & 1) : 0;
       uint8_t* staging = sm + p.off_staging + buf * p.st_buf_bytes;
+      // per 128-row sub-tile: pixel coordinates, validity, row offset in the destination tensor
+      bool valid_m[MT];
+      int64_t roff_m[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const int w = ti.w * bw_ + lw[m], h = ti.h * bh_ + lh[m], t = ti.t * bt_ + lt[m];
+        valid_m[m] = (w < dW_) && (h < dH_) && (t < dT_);
+        roff_m[m] = 0;
+        if (STATS != 1 && (p.has_addend || STATS == 2) && valid_m[m])
+          roff_m[m] = p.a_off + (int64_t)b * p.a_sb + (int64_t)t * p.a_st + (int64_t)h * p.a_sh + (int64_t)w * p.a_sw + n_idx * p.Ntile;
+      }
+      const bool valid0 = valid_m[0];
       // STATS == 2: this pixel's row of the producing layer's conv output, fetched before the accumulator wait
       uint4 yq[STATS == 2 ? 2 * RS : 1];
       if (STATS == 2) {
         const int nch = (cend - cbeg) >> 4;
-        const __nv_bfloat16* yrow = yprev + roff + cbeg;
+        const __nv_bfloat16* yrow = yprev + roff_m[0] + cbeg;   // (MT == 1 in this mode)
 #pragma unroll
         for (int j = 0; j < (STATS == 2 ? RS : 0); ++j) {
-          if (j < nch && valid) {
+          if (j < nch && valid0) {
             yq[2 * j] = *reinterpret_cast<const uint4*>(yrow + 16 * j);
             yq[2 * j + 1] = *reinterpret_cast<const uint4*>(yrow + 16 * j + 8);
           } else {
@@ -467,7 +494,14 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
       if (edbg) { const long long c2 = clock64(); w_a += c2 - c1; c1 = c2; }
 
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * p.Ntile) + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr0 = tmem_base + (uint32_t)(acc * MT * p.Ntile) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {   // not unrolled: one copy of the drain code for both sub-tiles
+      {
+      const bool valid = m ? valid_m[MT - 1] : valid_m[0];
+      const __nv_bfloat16* arow = (STATS != 1 && p.has_addend && valid) ? addend + (m ? roff_m[MT - 1] : roff_m[0]) : nullptr;
+      const uint32_t row_off = (uint32_t)((e + 128 * m) * p.st_rowbytes);
+      const uint32_t taddr = taddr0 + (uint32_t)(m * p.Ntile);
       auto store16 = [&](const float* f, int c) {   // 16 consecutive channels starting at channel c of this tile
         uint4 o0, o1;
         __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
@@ -573,6 +607,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (rem >= 64) emit16(vb + 16, c0c + 48);
         }
       }
+      }   // m < MT
+      }   // sub-tiles
       if (edbg) { const long long c2 = clock64(); w_b += c2 - c1; c1 = c2; }
       // accumulator drained: hand the TMEM buffer back to the MMA warp; publish the staged tile to the async proxy
       tc_fence_before();
@@ -723,7 +759,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64;
+static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64, g_opt_mt = 0;
 int tc_option(const char* name, int value, bool set) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_opt_halo;
@@ -741,6 +777,7 @@ int tc_option(const char* name, int value, bool set) {
   else if (!strcmp(name, "tc_tail")) slot = &g_opt_tail;
   else if (!strcmp(name, "tc_acc4")) slot = &g_opt_acc4;
   else if (!strcmp(name, "tc_bwd_stats_max")) slot = &g_opt_bwd_stats_max;
+  else if (!strcmp(name, "tc_mt")) slot = &g_opt_mt;
   if (slot == nullptr) return -1;
   if (set) *slot = value;
   return *slot;
@@ -774,7 +811,8 @@ struct TcPlan {
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, bool bwd_stats = false) {
+static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, bool bwd_stats, int MT) {
+  const int PT = 128 * MT;   // pixels per tile
   if (!g_opt_tc) return false;
   const int taps = g.kt * g.kh * g.kw;
   if (taps > TC_MAX_LOADS || taps < 1) return false;
@@ -786,6 +824,7 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, boo
   TcParams p;
   memset(&p, 0, sizeof(p));
   // N tiling
+  p.MT = MT;
   p.n_ntiles = (g.dC + 255) / 256;
   if (g.dC % (16 * p.n_ntiles)) return false;
   p.Ntile = g.dC / p.n_ntiles;
@@ -831,13 +870,14 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, boo
   p.cw_shift = chunked ? (p.cw == 64 ? 6 : (p.cw == 32 ? 5 : 4)) : -1;
   p.stat_M = p.Ntile <= 64 ? 64 : 128;
   p.st_rowbytes = p.cw * 2;
-  p.st_chunk_bytes = round_up(128 * p.st_rowbytes, 1024);
+  p.st_chunk_bytes = round_up(PT * p.st_rowbytes, 1024);
   p.st_chunks = (p.Ntile + p.cw - 1) / p.cw;
   if (p.mma_stats && p.st_chunks < p.stat_M / p.cw) p.st_chunks = p.stat_M / p.cw;   // the Gram A operand spans stat_M channels
   p.st_buf_bytes = p.st_chunks * p.st_chunk_bytes;
   // TMEM accumulators: the commit -> epilogue wake-up -> drain -> release -> next MMA round trip is ~1200 cycles, longer than a
   // short-K tile, so narrow tiles keep four accumulators in flight
-  p.acc_bufs = (p.mma_stats && 4 * p.Ntile > 512) ? 1 : ((!p.mma_stats && g_opt_acc4 && 4 * p.Ntile <= 512) ? 4 : 2);
+  p.acc_bufs = (p.mma_stats && 4 * p.Ntile > 512) ? 1 : ((!p.mma_stats && g_opt_acc4 && 4 * MT * p.Ntile <= 512) ? 4 : 2);
+  if (MT == 2 && (p.n_ntiles != 1 || p.mma_stats || (has_stats && !p.reg_stats) || bwd_stats || 2 * MT * p.Ntile > 512)) return false;
   const int wgt_total = used_taps * p.w_row_bytes;
   p.w_resident = (g_opt_resident && p.n_ntiles == 1 && wgt_total <= 98304) ? 1 : 0;
   const int stats_bytes = round_up(2 * g.dC * 4, 16);
@@ -853,9 +893,9 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, boo
   for (int mode = 0; mode < 3; ++mode) {
     if (mode == 1 && !(g_opt_halo && !strided && g.kt == 1 && g.kh > 1)) continue;
     if (mode == 2 && !(g_opt_halo && !strided && g.kh == 1 && g.kw == 1 && g.kt > 1)) continue;
-    for (int bw = 1; bw <= 128; bw <<= 1) {
-      for (int bh = 1; bh * bw <= 128; bh <<= 1) {
-        const int bt = 128 / (bw * bh);
+    for (int bw = 1; bw <= PT; bw <<= 1) {
+      for (int bh = 1; bh * bw <= PT; bh <<= 1) {
+        const int bt = PT / (bw * bh);
         if (mode == 1 && (bt != 1 || bw % 8)) continue;
         if (mode == 2 && ((bw * bh) % 8)) continue;
         if (bw * g.mw > 256 || bh * g.mh > 256 || bt * g.mt > 256) continue;
@@ -865,14 +905,14 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, boo
           if (bh >= 2 * g.dH && bh > 1) continue;
           if (bt >= 2 * g.dT && bt > 1) continue;
         }
-        int rows_l = 128, nloads = taps, nsub = 1;
+        int rows_l = PT, nloads = taps, nsub = 1;
         if (mode == 1) { rows_l = (bh + g.kh - 1) * bw; nloads = g.kw; nsub = g.kh; if (bh + g.kh - 1 > 256) continue; }
         if (mode == 2) { rows_l = (bt + g.kt - 1) * bh * bw; nloads = 1; nsub = g.kt; if (bt + g.kt - 1 > 256) continue; }
         const int stage = round_up(rows_l * rowbytes, 1024) + (p.w_resident ? 0 : nsub * p.b_sub_bytes);
         if (fixed - p.st_buf_bytes + 2 * stage > TC_SMEM_MAX) continue;
         const double ntiles = (double)((g.dW + bw - 1) / bw) * ((g.dH + bh - 1) / bh) * ((g.dT + bt - 1) / bt);
         const double cost = ntiles * ((double)nloads * p.ncblk * (rows_l * rowbytes + nsub * p.b_box_bytes) +
-                                      0.15 * taps * 128.0 * g.sC * 2.0) - 1e-3 * bw;
+                                      0.15 * taps * (double)PT * g.sC * 2.0) - 1e-3 * bw;
         if (cost < best) { best = cost; best_mode = mode; best_bw = bw; best_bh = bh; best_bt = bt; }
       }
     }
@@ -889,7 +929,7 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, boo
   p.dW = g.dW; p.dH = g.dH; p.dT = g.dT; p.dC = g.dC;
   p.mw = g.mw; p.mh = g.mh; p.mt = g.mt;
 
-  int rows_l = 128;
+  int rows_l = PT;
   out->a_estride[0] = 1; out->a_estride[1] = g.mw; out->a_estride[2] = g.mh; out->a_estride[3] = g.mt; out->a_estride[4] = 1;
   out->a_box[0] = p.CB; out->a_box[4] = 1;
   auto tap_index = [&](int jt, int jh, int jw) {
@@ -939,8 +979,9 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, boo
     return (lps % p.ncblk == 0) ? (lps / p.ncblk) * ((p.ncblk - 1) * p.slot_bytes + p.slot_bytes_t) : lps * p.slot_bytes;
   };
   int best_lps = 0, best_stages = 0;
+  long best_score = -1;
   auto search = [&]() {
-    long best_score = -1;
+    best_score = -1;
     best_lps = 0;
     const int avail = TC_SMEM_MAX - fixed_bytes();
     for (int lps = 1; lps <= total_loads && lps <= (g_opt_lps_max < 1 ? 1 : g_opt_lps_max); ++lps) {
@@ -955,11 +996,14 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, boo
     }
   };
   search();
-  if ((best_lps == 0 || best_stages < 3) && p.st_bufs == 2) {   // prefer pipeline depth over a second staging buffer
+  if (p.st_bufs == 2 && best_score < 1000000L) {   // a second staging buffer is worth less than two MMA warps / pipeline depth
     const int keep_lps = best_lps, keep_st = best_stages;
+    const long keep_score = best_score;
     p.st_bufs = 1;
     search();
-    if (best_lps == 0 || (keep_lps != 0 && best_stages <= keep_st)) { p.st_bufs = 2; best_lps = keep_lps; best_stages = keep_st; }
+    if (keep_lps != 0 && best_score / 100000L <= keep_score / 100000L) {   // keep two buffers unless one buys a better tier
+      p.st_bufs = 2; best_lps = keep_lps; best_stages = keep_st; best_score = keep_score;
+    }
   }
   if (best_lps == 0 && p.w_resident) {
     p.w_resident = 0;
@@ -979,7 +1023,7 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, boo
   p.off_scratch = p.off_stats + stats_bytes;
   p.off_bars = p.off_scratch + 16384;
   int cols = 32;
-  const int need_cols = (p.acc_bufs + (p.mma_stats ? 2 : 0)) * p.Ntile;
+  const int need_cols = (p.acc_bufs * MT + (p.mma_stats ? 2 : 0)) * p.Ntile;
   while (cols < need_cols) cols <<= 1;
   if (cols > 512) return false;
   p.tmem_cols = cols;
@@ -991,6 +1035,19 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, boo
   const int sms = num_sms();
   out->grid = p.num_tiles < sms ? p.num_tiles : sms;
   return out->smem <= (size_t)TC_SMEM_MAX;
+}
+
+// 256-pixel tiles (two 128-row MMA sub-tiles per handshake round) when they keep both MMA warps busy and leave enough
+// tiles per CTA; else the 128-pixel plan
+static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, bool bwd_stats = false) {
+  const bool ok1 = plan_gather_mt(g, has_stats, out, bwd_stats, 1);
+  if (g_opt_mt == 1) return ok1;
+  TcPlan big;
+  if (!plan_gather_mt(g, has_stats, &big, bwd_stats, 2)) return ok1;
+  // measured rule (scripts/role_variants.py): the larger tile wins unless it costs the second MMA-issuing warp
+  const bool take = g_opt_mt == 2 || !ok1 || (big.p.num_tiles >= 8 * num_sms() && big.p.dual_mma >= out->p.dual_mma);
+  if (take) *out = big;
+  return true;
 }
 
 static int encode_act_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int T, int B, const int* box,
@@ -1090,13 +1147,17 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   static cudaError_t attr_err = cudaSuccess;
   typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const __nv_bfloat16*, float*,
                          long long*, const __nv_bfloat16*, const float*);
-  static KernFn const kerns[13] = {tc_gather_gemm_kernel<0, 0>, tc_gather_gemm_kernel<1, 1>, tc_gather_gemm_kernel<2, 1>,
-                                   tc_gather_gemm_kernel<3, 1>, tc_gather_gemm_kernel<1, 0>, tc_gather_gemm_kernel<2, 0>,
-                                   tc_gather_gemm_kernel<3, 0>, tc_gather_gemm_kernel<4, 0>, tc_gather_gemm_kernel<5, 0>,
-                                   tc_gather_gemm_kernel<8, 0>, tc_gather_gemm_kernel<1, 2>, tc_gather_gemm_kernel<2, 2>,
-                                   tc_gather_gemm_kernel<3, 2>};
+  static KernFn const kerns[20] = {tc_gather_gemm_kernel<0, 0, 1>, tc_gather_gemm_kernel<1, 1, 1>, tc_gather_gemm_kernel<2, 1, 1>,
+                                   tc_gather_gemm_kernel<3, 1, 1>, tc_gather_gemm_kernel<1, 0, 1>, tc_gather_gemm_kernel<2, 0, 1>,
+                                   tc_gather_gemm_kernel<3, 0, 1>, tc_gather_gemm_kernel<4, 0, 1>, tc_gather_gemm_kernel<5, 0, 1>,
+                                   tc_gather_gemm_kernel<8, 0, 1>, tc_gather_gemm_kernel<1, 2, 1>, tc_gather_gemm_kernel<2, 2, 1>,
+                                   tc_gather_gemm_kernel<3, 2, 1>,
+                                   // 256-pixel tiles (Ntile <= 128, register statistics or none)
+                                   tc_gather_gemm_kernel<1, 1, 2>, tc_gather_gemm_kernel<2, 1, 2>, tc_gather_gemm_kernel<3, 1, 2>,
+                                   tc_gather_gemm_kernel<1, 0, 2>, tc_gather_gemm_kernel<2, 0, 2>, tc_gather_gemm_kernel<3, 0, 2>,
+                                   tc_gather_gemm_kernel<4, 0, 2>};
   std::call_once(attr_once, [] {
-    for (int i = 0; i < 13 && attr_err == cudaSuccess; ++i)
+    for (int i = 0; i < 20 && attr_err == cudaSuccess; ++i)
       attr_err = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
   });
   DP_REQUIRE(attr_err == cudaSuccess, DP_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s",
@@ -1107,11 +1168,15 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   else if (p.reg_stats) ki = p.drain_rs;                              // 1..3
   else if (p.drain_rs >= 1 && p.drain_rs <= 5) ki = 3 + p.drain_rs;   // 4..8
   else if (p.drain_rs >= 6 && p.drain_rs <= 8) ki = 9;
+  if (p.MT == 2) {
+    DP_REQUIRE(!bwd_stats && p.drain_rs >= 1 && p.drain_rs <= (p.reg_stats ? 3 : 4), DP_ERR_UNSUPPORTED, "tcgen05 conv: no 256-pixel kernel for this shape");
+    ki = p.reg_stats ? 12 + p.drain_rs : 15 + p.drain_rs;   // 13..15 / 16..19
+  }
   launch_pdl(kerns[ki], dim3(plan.grid), dim3(TC_THREADS), plan.smem, s, tmA, tmB, tmD, tmA2, tmB2, p, (const __nv_bfloat16*)addend, part, dbg,
              (const __nv_bfloat16*)yprev, bn_ss);
   if (getenv("DP_DEBUG_PLAN"))
-    fprintf(stderr, "[tc_gather] dst %dx%dx%dx%d src C=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d CB=%d ncblk=%d Ntile=%d stages=%d lps=%d dual=%d CBt=%d stats=%d/%d stage_bytes=%d a_box=%d tiles=%d grid=%d\n",
-            g.dT, g.dH, g.dW, g.dC, g.sC, g.kt * g.kh * g.kw, p.bw, p.bh, p.bt, p.nloads, p.nsub, p.CB, p.ncblk, p.Ntile, p.num_stages, p.lps, p.dual_mma, p.CBt, p.reg_stats * 10 + p.drain_rs, p.mma_stats,
+    fprintf(stderr, "[tc_gather] dst %dx%dx%dx%d src C=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d CB=%d ncblk=%d Ntile=%d MT=%d stages=%d lps=%d dual=%d CBt=%d stats=%d/%d stage_bytes=%d a_box=%d tiles=%d grid=%d\n",
+            g.dT, g.dH, g.dW, g.dC, g.sC, g.kt * g.kh * g.kw, p.bw, p.bh, p.bt, p.nloads, p.nsub, p.CB, p.ncblk, p.Ntile, p.MT, p.num_stages, p.lps, p.dual_mma, p.CBt, p.reg_stats * 10 + p.drain_rs, p.mma_stats,
             p.stage_bytes, p.a_box_bytes, p.num_tiles, plan.grid);
   if (nparts != nullptr) *nparts = plan.grid;
   return check_launch("tc_gather_gemm_kernel");
