@@ -855,7 +855,10 @@ static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, 
   p.reg_stats = (has_stats && (g_opt_reg_stats || bwd_stats) && p.n_ntiles == 1 && p.Ntile <= 96) ? 1 : 0;
   // the BN-backward sums exist only in the register mode, and only pay off up to 64 destination channels: each epilogue
   // thread reads its own pixel row of the producer's output (one 32-byte sector per lane and load), which at 80 channels
-  // costs more LSU wavefronts than the stand-alone reduction pass saves (measured: 1229 us fused vs 310 + 350 us)
+  // costs more LSU wavefronts than the stand-alone reduction pass saves (measured: 1229 us fused vs 310 + 350 us).
+  // Bringing the producer's tile in through TMA instead (ring of 4 tiles in the staging layout, read back from smem) was
+  // tried and is slower still at both 32 channels (889 vs 543 us) and 80 (952 vs 603 us composed): the 64-byte-row boxes
+  // and the extra per-tile work land on the single producer thread, which these short-K layers cannot spare.
   if (bwd_stats && (!p.reg_stats || p.Ntile > g_opt_bwd_stats_max)) return false;
   p.drain_rs = (!has_stats || p.reg_stats) ? ((p.Ntile >> 4) + 1) / 2 : 0;
   p.mma_stats = (has_stats && !p.reg_stats && g_opt_mma_stats && p.n_ntiles == 1 && p.Ntile <= 128) ? 1 : 0;
@@ -1045,7 +1048,9 @@ static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, boo
   TcPlan big;
   if (!plan_gather_mt(g, has_stats, &big, bwd_stats, 2)) return ok1;
   // measured rule (scripts/role_variants.py): the larger tile wins unless it costs the second MMA-issuing warp
-  const bool take = g_opt_mt == 2 || !ok1 || (big.p.num_tiles >= 8 * num_sms() && big.p.dual_mma >= out->p.dual_mma);
+  // (or keeps a deep pipeline: >= 5 single-load stages)
+  const bool take = g_opt_mt == 2 || !ok1 ||
+                    (big.p.num_tiles >= 8 * num_sms() && (big.p.dual_mma >= out->p.dual_mma || big.p.num_stages >= 5));
   if (take) *out = big;
   return true;
 }
