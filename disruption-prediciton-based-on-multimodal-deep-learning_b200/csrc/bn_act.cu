@@ -15,7 +15,7 @@ constexpr int RED_THREADS = 256;
 // ---- generic per-channel column reduction of two quantities over [rows][Cp] ----
 // F: __device__ void operator()(int64_t elem_offset, int c0, float* a8, float* b8) accumulates 8 channels
 template <typename F>
-__global__ void __launch_bounds__(RED_THREADS)
+__global__ void __launch_bounds__(RED_THREADS, 2)
 col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part) {  // f by value: per-thread register copy
   pdl_launch_dependents();
   pdl_wait();
@@ -35,7 +35,11 @@ col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part) {  // f 
     const int cv = tid % vpr, rl = tid / vpr;
     f.init(cv * 8);                       // this thread's 8 channels never change: parameters live in registers
     int64_t r = r0 + rl;
-    for (; r + 3 * rpi < r1; r += 4 * rpi) {  // four independent rows in flight
+    for (; r + 7 * rpi < r1; r += 8 * rpi) {  // eight independent rows in flight (two CTAs of 256 threads per SM)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f((r + u * rpi) * Cp + cv * 8, a, b);
+    }
+    for (; r + 3 * rpi < r1; r += 4 * rpi) {
       f(r * Cp + cv * 8, a, b);
       f((r + rpi) * Cp + cv * 8, a, b);
       f((r + 2 * rpi) * Cp + cv * 8, a, b);
