@@ -71,6 +71,8 @@ DP_API int dp_pack_weights(const dp_conv_desc* d, const float* w, void* w_fwd, v
 
 DP_API int dp_conv_supported(const dp_conv_desc* d, int op, int impl) {
   if (validate(d) != DP_OK) return 0;
+  if (op == 3)   // is dp_conv_dgrad_bnstats fused in the tcgen05 epilogue (1) or composed of dgrad + reduction (0)?
+    return (resolve_impl(d, 1, impl) == DP_IMPL_TC && tc_dgrad_bnstats_supported(d)) ? 1 : 0;
   if (op < 0 || op > 2) return 0;
   return resolve_impl(d, op, impl) > 0 ? 1 : 0;
 }

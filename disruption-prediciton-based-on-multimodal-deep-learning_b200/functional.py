@@ -180,6 +180,18 @@ class ConvGeom:
 
 
 _GEOMS = {}
+_FUSED = {}
+
+
+def _fused_bnstats(geom: "ConvGeom") -> bool:
+    """True when the data gradient of this geometry produces the producer's BatchNorm-backward sums in its epilogue
+    (otherwise the stand-alone reduction runs in the producer's own backward, as without the fusion)."""
+    key = (id(geom), _STATE["impl"])
+    r = _FUSED.get(key)
+    if r is None:
+        r = bool(L.load().dp_conv_supported(C.byref(geom.desc), 3, _STATE["impl"]))
+        _FUSED[key] = r
+    return r
 
 
 def conv_geom(C_in, K, kernel, stride, padding, x: torch.Tensor) -> ConvGeom:
@@ -752,7 +764,7 @@ class ResBlockFn(torch.autograd.Function):
             geom, cfg, wshape = ctx.metas[slot]
             box = []
             next_bn = None
-            if nxt is not None and fuse and need_dx:
+            if nxt is not None and fuse and need_dx and _fused_bnstats(geom):
                 _, y_n, stats_n, _ = sv[nxt]
                 next_bn = (y_n, stats_n, ctx.metas[nxt][1].slope, box)
             res = layer_backward((xs, y, out if with_out else None, stats, wd, geom), dz, wshape, cfg, ctx.training,

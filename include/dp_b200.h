@@ -94,7 +94,7 @@ int dp_u8_frames_to_ndhwc(const uint8_t* src, void* dst, const float* mean3, int
 int dp_pack_weights(const dp_conv_desc* d, const float* w, void* w_fwd, void* w_dgrad, void* stream);
 
 /* ---- convolution: forward / dgrad / wgrad (replace cuDNN behind nn.Conv3d, R2Plus1D.py:44-51,57) ---- */
-int dp_conv_supported(const dp_conv_desc* d, int op /*0 fwd,1 dgrad,2 wgrad*/, int impl);
+int dp_conv_supported(const dp_conv_desc* d, int op /*0 fwd,1 dgrad,2 wgrad,3 dgrad_bnstats fused in the epilogue*/, int impl);
 /* y = conv(x, w).  If `part` is non-NULL, per-channel (sum, sumsq) partials of y
  * are written to part[nparts][2][Kp] and *nparts is set (<= DP_MAX_PARTS). */
 int dp_conv_fwd(const dp_conv_desc* d, const void* x, const void* w_fwd, void* y,
