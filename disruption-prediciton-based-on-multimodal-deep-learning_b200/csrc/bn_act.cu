@@ -128,10 +128,24 @@ __device__ __forceinline__ void fin_reduce(const float* __restrict__ part, int n
                                            double& S, double& Q, double (*red)[FIN_PL][FIN_CH]) {
   double s = 0.0, q = 0.0;
   if (cval) {
-    for (int p = pl; p < nparts; p += FIN_PL) {
+    // four independent load/accumulate chains per thread: the loop is pure memory latency (<= 592 partials), and this
+    // kernel sits on the critical path between every conv and its apply pass; the order stays fixed (deterministic)
+    double s1 = 0.0, q1 = 0.0, s2 = 0.0, q2 = 0.0, s3 = 0.0, q3 = 0.0;
+    int p = pl;
+    for (; p + 3 * FIN_PL < nparts; p += 4 * FIN_PL) {
+      const float a0 = part[((int64_t)p * 2 + 0) * Cp + c], b0 = part[((int64_t)p * 2 + 1) * Cp + c];
+      const float a1 = part[((int64_t)(p + FIN_PL) * 2 + 0) * Cp + c], b1 = part[((int64_t)(p + FIN_PL) * 2 + 1) * Cp + c];
+      const float a2 = part[((int64_t)(p + 2 * FIN_PL) * 2 + 0) * Cp + c], b2 = part[((int64_t)(p + 2 * FIN_PL) * 2 + 1) * Cp + c];
+      const float a3 = part[((int64_t)(p + 3 * FIN_PL) * 2 + 0) * Cp + c], b3 = part[((int64_t)(p + 3 * FIN_PL) * 2 + 1) * Cp + c];
+      s += (double)a0; q += (double)b0; s1 += (double)a1; q1 += (double)b1;
+      s2 += (double)a2; q2 += (double)b2; s3 += (double)a3; q3 += (double)b3;
+    }
+    for (; p < nparts; p += FIN_PL) {
       s += (double)part[((int64_t)p * 2 + 0) * Cp + c];
       q += (double)part[((int64_t)p * 2 + 1) * Cp + c];
     }
+    s = (s + s1) + (s2 + s3);
+    q = (q + q1) + (q2 + q3);
   }
   const int cl = threadIdx.x % FIN_CH;
   red[0][pl][cl] = s;

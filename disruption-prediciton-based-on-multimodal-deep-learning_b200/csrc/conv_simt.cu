@@ -179,34 +179,52 @@ wgrad_kernel(Geom g, const T* __restrict__ x, const T* __restrict__ dy, float* _
 
 // dw[k][c][tap] (PyTorch (K,C,kt,kh,kw) order) = sum_split partial[split][k][tap][c], splits added in a fixed
 // order (deterministic).  Threads run along c, so every split's read is a coalesced row.
-__global__ void __launch_bounds__(256)
+constexpr int WR_LANES = 8;    // split-lanes per output element
+constexpr int WR_ELEMS = 32;   // consecutive elements (along c) per CTA
+__global__ void __launch_bounds__(WR_LANES * WR_ELEMS)
 wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                     int nsplit, int K, int C, int Kp, int Cp, int taps) {
   pdl_launch_dependents();
   pdl_wait();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // 8 lanes share the <= 295 splits of one element (the loop is pure load latency), each with four independent chains;
+  // lanes and chains are combined in a fixed order, so the result is deterministic
+  __shared__ float red[WR_LANES][WR_ELEMS];
+  const int el = threadIdx.x % WR_ELEMS, ln = threadIdx.x / WR_ELEMS;
+  const int idx = blockIdx.x * WR_ELEMS + el;
   const int total = K * taps * Cp;
-  if (idx >= total) return;
-  const int c = idx % Cp, tap = (idx / Cp) % taps, k = idx / (Cp * taps);
-  if (c >= C) return;
-  const int64_t stride = (int64_t)Kp * taps * Cp;
-  const float* p = partial + idx;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int i = 0;
-  for (; i + 4 <= nsplit; i += 4) {
-    s0 += p[(int64_t)i * stride];
-    s1 += p[(int64_t)(i + 1) * stride];
-    s2 += p[(int64_t)(i + 2) * stride];
-    s3 += p[(int64_t)(i + 3) * stride];
+  float acc = 0.f;
+  if (idx < total) {
+    const int64_t stride = (int64_t)Kp * taps * Cp;
+    const float* p = partial + idx;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int i = ln;
+    for (; i + 3 * WR_LANES < nsplit; i += 4 * WR_LANES) {
+      s0 += p[(int64_t)i * stride];
+      s1 += p[(int64_t)(i + WR_LANES) * stride];
+      s2 += p[(int64_t)(i + 2 * WR_LANES) * stride];
+      s3 += p[(int64_t)(i + 3 * WR_LANES) * stride];
+    }
+    for (; i < nsplit; i += WR_LANES) s0 += p[(int64_t)i * stride];
+    acc = (s0 + s1) + (s2 + s3);
   }
-  for (; i < nsplit; ++i) s0 += p[(int64_t)i * stride];
-  dw[((int64_t)k * C + c) * taps + tap] = (s0 + s1) + (s2 + s3);
+  red[ln][el] = acc;
+  __syncthreads();
+  if (ln == 0 && idx < total) {
+    const int c = idx % Cp, tap = (idx / Cp) % taps, k = idx / (Cp * taps);
+    if (c < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < WR_LANES; ++j) t += red[j][el];
+      dw[((int64_t)k * C + c) * taps + tap] = t;
+    }
+  }
 }
 
 int wgrad_reduce_launch(const float* partial, float* dw, int nsplit, int K, int C, int Kp, int Cp, int taps,
                         cudaStream_t s) {
   const int total = K * taps * Cp;
-  launch_pdl(wgrad_reduce_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, s, partial, dw, nsplit, K, C, Kp, Cp, taps);
+  launch_pdl(wgrad_reduce_kernel, dim3(ceil_div(total, WR_ELEMS)), dim3(WR_LANES * WR_ELEMS), 0, s, partial, dw, nsplit, K, C, Kp,
+             Cp, taps);
   return check_launch("conv_wgrad_reduce");
 }
 
