@@ -6,16 +6,25 @@
 // and as   dgrad    (src = dy, wgt = w_dgrad[Cp][taps][Kp], dst = dx, taps flipped, optional addend)
 // for the nn.Conv3d calls at /root/reference/src/models/R2Plus1D.py:44-51,57 and their autograd.
 //
-// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
-//   warp 0 lane 0 : TMA producer. NDHWC activations are a 5-D tensor map (C,W,H,T,B); one box =
-//                   128 output pixels (bw x bh x bt) x CB channels, zero-filled outside the tensor, so
-//                   padding costs nothing.  Stride-1 convs load ONE halo box per kw (or one for all
-//                   kt) and reuse it for the kh (kt) taps by moving the UMMA descriptor start row.
-//   warp 1 lane 0 : issues tcgen05.mma (M=128, N=Ntile<=256, K=16) into a double-buffered TMEM
-//                   accumulator; tcgen05.commit releases smem stages and publishes the accumulator.
-//   warp 2        : TMEM allocate / free.
-//   warps 4-7     : epilogue: tcgen05.ld -> (+addend) -> bf16 -> smem staging -> TMA store (clips the
-//                   tensor edge), per-channel sum / sum-of-squares for BatchNorm from the staged tile.
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised; tile = 128 * MT output pixels):
+//   warp 0 lane 0 : TMA producer. NDHWC activations are a 5-D tensor map (C,W,H,T,B); one box = one tile of pixels
+//                   (bw x bh x bt) x CB channels, zero-filled outside the tensor, so padding costs nothing.  Stride-1
+//                   convs load ONE halo box per kw (or one for all kt) and reuse it for the kh (kt) taps by moving
+//                   the UMMA descriptor start row.  The last channel block of C % 64 in {16, 32} is a narrow box with
+//                   its own swizzle.  A pipeline stage carries `lps` loads (a whole tile where smem allows) and is
+//                   armed (expect_tx) after its copies are issued.
+//   warps 1, 2    : issue tcgen05.mma (M=128, N=Ntile<=256, K=16) into 2-4 TMEM accumulators.  In dual mode the two
+//                   warps take alternate tiles, each on a PRIVATE ring of stages (a parity wait cannot tell phase k+1
+//                   from k-1, so two consumers never share an mbarrier); tcgen05.commit releases the stage and
+//                   publishes the accumulator.  Warp 2 also allocates / frees TMEM.
+//   warp 3        : TMA store of the staged tile (clips the tensor edge); publishes "buffer free" through a counter
+//                   in shared memory.
+//   warps 4-11    : epilogue, two warps per TMEM lane quadrant, each draining half of the columns:
+//                   tcgen05.ld -> (+addend) -> bf16 -> swizzled staging tile.  BatchNorm statistics (forward) and the
+//                   producer's BatchNorm-backward sums (dgrad) are accumulated in registers from the fp32 accumulators;
+//                   wide tiles fall back to Gram / ones MMAs in TMEM or to the CUDA cores.
+// Hand-offs that the hardware does not force onto mbarriers (epilogue <-> store warp <-> MMA warps) use named barriers:
+// every mbarrier operation occupies its thread for ~200 cycles on B200 (scripts/ubench/sync_ops.cu).
 #include "dp_common.cuh"
 #include "conv_internal.cuh"
 #include "tc_ptx.cuh"
@@ -27,7 +36,7 @@ namespace dp {
 using namespace ptx;
 
 constexpr int TC_MAX_LOADS = 49;
-constexpr int TC_THREADS = 384;   // warps: 0 TMA loads, 1 MMA, 2 TMEM alloc, 3 TMA stores, 4-11 epilogue
+constexpr int TC_THREADS = 384;   // warps: 0 TMA loads, 1-2 MMA (2 also TMEM alloc), 3 TMA stores, 4-11 epilogue
 constexpr int TC_EPI = 256;       // two epilogue warps per TMEM lane quadrant, each drains half of the columns
 constexpr int TC_SMEM_MAX = 232448;  // 227 KB opt-in limit per CTA
 
