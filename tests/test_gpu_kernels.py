@@ -467,3 +467,21 @@ def test_dgrad_bnstats(geom, slope, use_add):
     e1 = float((st[1, :Cc] - s1).abs().max() / scale1)
     assert e0 < 2e-3 and e1 < 2e-3, (e0, e1)
     assert float(st[:, Cc:].abs().max()) == 0.0 if d.Cp > Cc else True
+
+
+@pytest.mark.parametrize("opts", [{"tc_mt": 1}, {"tc_mt": 2}, {"tc_dual_mma": 0}, {"tc_tail": 0}, {"tc_acc4": 0},
+                                  {"tc_lps_max": 1}, {"tc_reg_stats": 0}, {"tc_st_bufs": 1}],
+                         ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
+def test_conv_tcgen05_plan_variants(opts):
+    """Every pipeline shape the planner can pick (128- / 256-pixel tiles, one or two MMA-issuing warps, narrow tail block
+    on or off, 2 or 4 accumulators, one load or a whole tile per stage, statistics in registers or on the tensor core,
+    one or two staging buffers) must give the same results against the fp64 reference."""
+    defaults = {k: L.get_option(k) for k in opts}
+    try:
+        for k, v in opts.items():
+            L.set_option(k, v)
+        for geom in (GEOMS_BIG[0], GEOMS_BIG[1], GEOMS_BIG[2], GEOMS_BIG[4], GEOMS_BIG[9]):
+            _tc_check(geom, B=1, seed=7)
+    finally:
+        for k, v in defaults.items():
+            L.set_option(k, v)
