@@ -208,3 +208,50 @@ def test_slowfast_surface_cpu(golden_dir):
     assert torch.allclose(sd["encoder.fastnet.layer1.0.bn1.running_var"], torch.full((4,), 0.9))
     assert torch.allclose(sd["encoder.slownet.layer0.1.running_mean"], 0.1 * sd["encoder.slownet.layer0.0.bias"])
     assert m.classifier.classifier[0].in_features == 640
+
+
+def test_every_layer_of_the_benchmark_has_a_tcgen05_plan():
+    """Planner regression guard (runs without a GPU: the plan only needs the SM count): at the benchmark's shapes
+    (B = 64, (3,21,128,128), [1,2,2,1]) every convolution must be served by the tcgen05 family in forward, data
+    gradient and weight gradient -- a planner change that silently dropped a layer to the CUDA-core kernels cost 2x
+    once -- and the stem must take its packed-rows fast path."""
+    import ctypes as C
+    from dp_b200 import _lib as L
+    from dp_b200 import functional as Fn
+    from oracle import r2plus1d_port as port
+
+    lib = L.load()
+
+    def out_dim(n, k, s, p):
+        return (n + 2 * p - k) // s + 1
+
+    stem, blocks = port.encoder_plan([1, 2, 2, 1], 1.0)
+    seq = []
+
+    def run_seq(layers, inp):
+        for (name, cin, cout, k, s, p, slope) in layers:
+            seq.append((name, cin, cout, k, s, p, inp))
+            inp = tuple(out_dim(inp[i], k[i], s[i], p[i]) for i in range(3))
+        return inp
+
+    cur = run_seq(stem, (21, 128, 128))
+    for b in blocks:
+        o = run_seq(b["conv1"], cur)
+        o = run_seq(b["conv2"], o)
+        if b["shortcut"]:
+            run_seq(b["shortcut"], cur)
+        cur = o
+    assert len(seq) == 32
+    B = 64
+    missing = []
+    for (name, cin, cout, k, s, p, (T, H, W)) in seq:
+        To, Ho, Wo = (out_dim(n, k[i], s[i], p[i]) for i, n in enumerate((T, H, W)))
+        d = L.ConvDesc(B, T, H, W, cin, Fn.ceil16(cin), To, Ho, Wo, cout, Fn.ceil16(cout), *k, *s, *p, L.DP_BF16)
+        if cin == 3:
+            if not lib.dp_stem_supported(C.byref(d)):
+                missing.append((name, "stem fast path"))
+            continue
+        for op, what in enumerate(("fwd", "dgrad", "wgrad")):
+            if not lib.dp_conv_supported(C.byref(d), op, L.IMPL_TC):
+                missing.append((name, what))
+    assert not missing, missing
