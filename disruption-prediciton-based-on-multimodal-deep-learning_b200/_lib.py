@@ -43,6 +43,8 @@ SIGNATURES = {
     "dp_device_check": (_i, []),
     "dp_num_sms": (_i, []),
     "dp_launch_count": (C.c_ulonglong, []),
+    "dp_simt_launch_count": (C.c_ulonglong, []),
+    "dp_simt_fallback_count": (C.c_ulonglong, []),
     "dp_set_option": (_i, [C.c_char_p, _i]),
     "dp_get_option": (_i, [C.c_char_p]),
     "dp_set_debug_buffer": (_i, [_vp, _sz]),
@@ -52,6 +54,7 @@ SIGNATURES = {
     "dp_pack_weights": (_i, [_pdesc, _vp, _vp, _vp, _vp]),
     "dp_conv_supported": (_i, [_pdesc, _i, _i]),
     "dp_conv_fwd": (_i, [_pdesc, _vp, _vp, _vp, _vp, _pint, _i, _vp]),
+    "dp_conv_fwd_bnact": (_i, [_pdesc, C.POINTER(C.c_longlong), _vp, _vp, _vp, _f, _vp, _f, _vp, _i, _vp]),
     "dp_conv_dgrad": (_i, [_pdesc, _vp, _vp, _vp, _vp, _i, _vp]),
     "dp_conv_dgrad_bnstats": (_i, [_pdesc, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _pint, _i, _vp]),
     "dp_conv_wgrad_workspace": (_sz, [_pdesc, _i]),
@@ -62,6 +65,7 @@ SIGNATURES = {
     "dp_stem_pack_input_u8": (_i, [_pdesc, _vp, C.POINTER(C.c_float), _vp, _vp]),
     "dp_stem_pack_weights": (_i, [_pdesc, _vp, _vp, _vp]),
     "dp_stem_conv_fwd": (_i, [_pdesc, _vp, _vp, _vp, _vp, _pint, _vp]),
+    "dp_stem_conv_fwd_bnact": (_i, [_pdesc, _vp, _vp, _vp, _f, _vp, _vp]),
     "dp_stem_wgrad_workspace": (_sz, [_pdesc]),
     "dp_stem_conv_wgrad": (_i, [_pdesc, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dp_bn_stats": (_i, [_vp, _i64, _i, _i, _vp, _pint, _vp]),
@@ -74,10 +78,18 @@ SIGNATURES = {
     "dp_add": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "dp_avgpool_fwd": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _vp]),
     "dp_avgpool_bwd": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _vp]),
+    "dp_se_swish_fwd": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
+    "dp_se_swish_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _vp]),
+    "dp_maxpool_hw_fwd": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "dp_maxpool_hw_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "dp_concat_channels": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "dp_split_channels": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "dp_loss_workspace": (_sz, [_i64]),
     "dp_loss_fwd_bwd": (_i, [_i, _vp, _vp, _vp, _vp, _f, _f, _i64, _i, _vp, _vp, _vp, _vp]),
     "dp_loss_bwd_scale": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "dp_optim_workspace": (_sz, [_i64]),
+    "dp_grad_sqnorm": (_i, [_vp, _i64, _f, _i, _vp, _vp, _vp]),
+    "dp_adamw_apply": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _f, _vp, _vp, _vp]),
     "dp_clip_adamw_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _f, _vp, _vp, _vp]),
 }
 

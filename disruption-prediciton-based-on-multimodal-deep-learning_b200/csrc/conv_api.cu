@@ -37,8 +37,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, T* __restrict__
   if (wd != nullptr) wd[((int64_t)c * taps + tap) * Kp + n] = (T)v;
 }
 
+unsigned long long g_simt_launches = 0;   // conv launches served by the CUDA-core family (dp_simt_launch_count)
+unsigned long long g_simt_fallbacks = 0;  // ... of which DP_IMPL_AUTO fell back from tcgen05 on a bf16 tensor
+int g_strict_tc = 0;                      // option "strict_tc": DP_IMPL_AUTO refuses to fall back in bf16
+
 static int resolve_impl(const dp_conv_desc* d, int op, int impl) {
-  if (impl == DP_IMPL_SIMT) return DP_IMPL_SIMT;
+  if (impl == DP_IMPL_SIMT) { ++g_simt_launches; return DP_IMPL_SIMT; }
   bool ok = false;
   if (d->dtype == DP_BF16) {
     if (op == 0) ok = tc_fwd_supported(d);
@@ -46,7 +50,24 @@ static int resolve_impl(const dp_conv_desc* d, int op, int impl) {
     else ok = tc_wgrad_supported(d);
   }
   if (impl == DP_IMPL_TC) return ok ? DP_IMPL_TC : -1;
-  return ok ? DP_IMPL_TC : DP_IMPL_SIMT;
+  if (ok) return DP_IMPL_TC;
+  // DP_IMPL_AUTO and the tcgen05 planner declined: the CUDA-core family serves the call.  That is the fp32 validation
+  // mode's normal path; on a bf16 tensor it is a silent slow path, so it is counted (bench.py reports it, must be 0)
+  // and refused outright under the "strict_tc" option.
+  if (d->dtype == DP_BF16) {
+    if (g_strict_tc) return -1;
+    ++g_simt_fallbacks;
+  }
+  ++g_simt_launches;
+  return DP_IMPL_SIMT;
+}
+
+// queries (dp_conv_supported, workspace sizing) must not disturb the counters
+static int resolve_impl_query(const dp_conv_desc* d, int op, int impl) {
+  const unsigned long long a = g_simt_launches, b = g_simt_fallbacks;
+  const int r = resolve_impl(d, op, impl);
+  g_simt_launches = a; g_simt_fallbacks = b;
+  return r;
 }
 
 }  // namespace dp
@@ -72,9 +93,11 @@ DP_API int dp_pack_weights(const dp_conv_desc* d, const float* w, void* w_fwd, v
 DP_API int dp_conv_supported(const dp_conv_desc* d, int op, int impl) {
   if (validate(d) != DP_OK) return 0;
   if (op == 3)   // is dp_conv_dgrad_bnstats fused in the tcgen05 epilogue (1) or composed of dgrad + reduction (0)?
-    return (resolve_impl(d, 1, impl) == DP_IMPL_TC && tc_dgrad_bnstats_supported(d)) ? 1 : 0;
+    return (resolve_impl_query(d, 1, impl) == DP_IMPL_TC && tc_dgrad_bnstats_supported(d)) ? 1 : 0;
+  if (op == 4)   // eval-mode fused conv + BatchNorm + LeakyReLU epilogue on the tcgen05 family
+    return (impl != DP_IMPL_SIMT && tc_fwd_bnact_supported(d)) ? 1 : 0;
   if (op < 0 || op > 2) return 0;
-  return resolve_impl(d, op, impl) > 0 ? 1 : 0;
+  return resolve_impl_query(d, op, impl) > 0 ? 1 : 0;
 }
 
 DP_API int dp_conv_fwd(const dp_conv_desc* d, const void* x, const void* w_fwd, void* y, float* part, int* nparts,
@@ -94,6 +117,30 @@ DP_API int dp_conv_fwd(const dp_conv_desc* d, const void* x, const void* w_fwd, 
     return bn_stats_launch(y, rows, d->Kp, d->dtype, part, nparts, s);
   }
   return DP_OK;
+}
+
+DP_API unsigned long long dp_simt_launch_count(void) { return g_simt_launches; }
+DP_API unsigned long long dp_simt_fallback_count(void) { return g_simt_fallbacks; }
+
+DP_API int dp_conv_fwd_bnact(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* w_fwd,
+                             const float* scale_shift, float slope, const void* residual, float slope_res, void* z,
+                             int impl, void* stream) {
+  int rc = validate(d);
+  if (rc != DP_OK) return rc;
+  DP_REQUIRE(x && w_fwd && z && scale_shift, DP_ERR_SHAPE, "dp_conv_fwd_bnact: NULL pointer");
+  cudaStream_t s = as_stream(stream);
+  if (impl != DP_IMPL_SIMT && tc_fwd_bnact_supported(d))
+    return tc_conv_fwd_bnact(d, xstrides, x, w_fwd, scale_shift, slope, residual, slope_res, z, s);
+  DP_REQUIRE(impl != DP_IMPL_TC && !(g_strict_tc && d->dtype == DP_BF16), DP_ERR_UNSUPPORTED,
+             "dp_conv_fwd_bnact: geometry not covered by the tcgen05 family");
+  DP_REQUIRE(xstrides == nullptr, DP_ERR_UNSUPPORTED, "dp_conv_fwd_bnact: input views need the tcgen05 family");
+  // CUDA-core composition (fp32 validation mode): conv into z, then the affine + activation pass in place
+  ++g_simt_launches;
+  if (d->dtype == DP_BF16) ++g_simt_fallbacks;
+  rc = simt_conv_fwd(d, x, w_fwd, z, s);
+  if (rc != DP_OK) return rc;
+  const int64_t rows = (int64_t)d->B * d->To * d->Ho * d->Wo;
+  return dp_bn_act_apply(z, scale_shift, scale_shift + d->Kp, slope, residual, slope_res, z, rows, d->Kp, d->dtype, stream);
 }
 
 DP_API int dp_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx,
@@ -130,7 +177,7 @@ DP_API int dp_conv_dgrad_bnstats(const dp_conv_desc* d, const void* dy, const vo
 DP_API size_t dp_conv_wgrad_workspace(const dp_conv_desc* d, int impl) {
   if (validate(d) != DP_OK) return 0;
   size_t a = simt_wgrad_workspace(d);
-  if (impl != DP_IMPL_SIMT && d->dtype == DP_BF16 && tc_wgrad_supported(d)) {
+  if (impl != DP_IMPL_SIMT && d->dtype == DP_BF16 && tc_wgrad_supported(d)) {  // (sizing query: no counters)
     size_t b = tc_wgrad_workspace(d);
     if (b > a) a = b;
   }

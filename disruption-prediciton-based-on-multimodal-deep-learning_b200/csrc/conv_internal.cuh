@@ -14,6 +14,7 @@ size_t simt_wgrad_workspace(const dp_conv_desc* d);
 // dw (K,C,taps) = sum over splits of partial[split][Kp][taps][Cp], fixed order
 int wgrad_reduce_launch(const float* partial, float* dw, int nsplit, int K, int C, int Kp, int Cp, int taps,
                         cudaStream_t s);
+extern int g_strict_tc;   // conv_api.cu: DP_IMPL_AUTO refuses the CUDA-core fallback on bf16 tensors
 int wg_option(const char* name, int value, bool set);
 int tc_option(const char* name, int value, bool set);
 
@@ -40,6 +41,11 @@ int tc_conv_fwd_view(const dp_conv_desc* d, const long long* xstrides, const voi
                      float* part, int* nparts, cudaStream_t s);
 int tc_conv_wgrad_view(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* dy, float* dw,
                        void* ws, size_t ws_bytes, cudaStream_t s);
+
+// eval-mode fused Conv3d -> BatchNorm(running statistics) -> LeakyReLU [-> + residual -> LeakyReLU] (no statistics)
+bool tc_fwd_bnact_supported(const dp_conv_desc* d);
+int tc_conv_fwd_bnact(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* w, const float* scale_shift,
+                      float slope, const void* residual, float slope_res, void* z, cudaStream_t s);
 
 // BN partial statistics over a finished tensor (bn_act.cu)
 int bn_stats_launch(const void* y, int64_t rows, int Cp, int dtype, float* part, int* nparts, cudaStream_t s);

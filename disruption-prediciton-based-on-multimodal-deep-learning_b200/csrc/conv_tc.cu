@@ -66,7 +66,11 @@ struct TcParams {
   int off_staging, off_ones, off_stats, off_scratch, off_bars;
   int tmem_cols, layout_type, sbo_bytes;
   int has_stats, has_addend;
-  float slope;   // STATS == 2: LeakyReLU slope of the producing layer
+  float slope;   // STATS == 2: LeakyReLU slope of the producing layer; epi_bn: slope of this layer's activation
+  // eval-mode fused epilogue (BatchNorm with running statistics folded into a per-channel affine, STATS == 0 only):
+  //   v = lrelu(acc * scale[c] + shift[c], slope);  with an addend (the residual):  v = lrelu(v + addend, slope_res)
+  int epi_bn;
+  float slope_res;
   int dbg_skip;  // development: 1 = no epilogue data movement / stores, 2 = no TMA loads, 4 = one MMA per load
   long long a_off, a_sw, a_sh, a_st, a_sb;  // addend view: element offset / strides of (w,h,t,b) in the dst tensor
   signed char off_w[TC_MAX_LOADS], off_h[TC_MAX_LOADS], off_t[TC_MAX_LOADS];
@@ -157,8 +161,6 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int e0 = threadIdx.x - (TC_THREADS - TC_EPI);
     if (p.has_stats && !p.mma_stats && !STATS)
       for (int i = e0; i < 2 * p.dC; i += TC_EPI) stats_sm[i] = 0.f;
-    if (STATS == 2)   // scale[dC], shift[dC] of the producing layer's BatchNorm
-      for (int i = e0; i < 2 * p.dC; i += TC_EPI) stats_sm[i] = bn_ss[i];
     if (p.mma_stats) {   // the all-ones A operand of the column-sum MMA (any canonical layout: every element is 1)
       uint32_t* ones = reinterpret_cast<uint32_t*>(sm + p.off_ones);
       for (int i = e0; i < 512; i += TC_EPI) ones[i] = 0x3F803F80u;
@@ -424,6 +426,13 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) tma_store_wait_all();
   } else if (warp >= 4) {
     if (STATS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    if (STATS == 2 || (STATS == 0 && p.epi_bn)) {   // scale[dC], shift[dC] (global memory: after pdl_wait)
+      for (int i = threadIdx.x - (TC_THREADS - TC_EPI); i < 2 * p.dC; i += TC_EPI) stats_sm[i] = bn_ss[i];
+      named_bar_sync(1, TC_EPI);
+    }
+    const bool epi_bn = STATS == 0 && p.epi_bn != 0;
+    const float* const ep_sc = stats_sm + 0;          // indexed by absolute destination channel
+    const float* const ep_sh = stats_sm + p.dC;
     // ===================== epilogue: TMEM -> bf16 -> swizzled staging tile =====================
     const int et = threadIdx.x - (TC_THREADS - TC_EPI);  // 0..255
     const int q = warp & 3;                              // TMEM lane quadrant this warp may access
@@ -533,10 +542,19 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = valid ? __uint_as_float(v[j]) : 0.f;
+        if (epi_bn) {
+          const int cg = n_idx * p.Ntile + c;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = lrelu(fmaf(f[j], ep_sc[cg + j], ep_sh[cg + j]), p.slope);
+        }
         if (arow != nullptr) {
           const f8 a0 = ld8(arow + c), a1 = ld8(arow + c + 8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { f[j] += a0.v[j]; f[8 + j] += a1.v[j]; }
+          if (epi_bn) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = lrelu(f[j], p.slope_res);
+          }
         }
         store16(f, c);
       };
@@ -562,11 +580,20 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 float f[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) f[k] = valid ? __uint_as_float(v[jj][k]) : 0.f;
+                if (STATS == 0 && epi_bn) {
+                  const int c = n_idx * p.Ntile + cbeg + 16 * (j0 + jj);   // destination channel
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) f[k] = lrelu(fmaf(f[k], ep_sc[c + k], ep_sh[c + k]), p.slope);
+                }
                 if (STATS != 1 && arow != nullptr) {
                   const int c = cbeg + 16 * (j0 + jj);
                   const f8 a0 = ld8(arow + c), a1 = ld8(arow + c + 8);
 #pragma unroll
                   for (int k = 0; k < 8; ++k) { f[k] += a0.v[k]; f[8 + k] += a1.v[k]; }
+                  if (STATS == 0 && epi_bn) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) f[k] = lrelu(f[k], p.slope_res);
+                  }
                 }
                 if (STATS == 1) {
                   const int js = (j0 + jj < NS) ? j0 + jj : 0;
@@ -1119,7 +1146,7 @@ static int encode_wgt_map(CUtensorMap* m, const void* ptr, int Ktot, int rows, i
 
 static int launch_gather(const GatherProblem& g, const void* src, const void* wgt, void* dst, const void* addend,
                          float* part, int* nparts, cudaStream_t s, const void* yprev = nullptr, const float* bn_ss = nullptr,
-                         float slope = 1.f) {
+                         float slope = 1.f, int epi_bn = 0, float slope_res = 1.f) {
   TcPlan plan;
   const bool bwd_stats = yprev != nullptr;
   DP_REQUIRE(plan_gather(g, part != nullptr, &plan, bwd_stats), DP_ERR_UNSUPPORTED, "tcgen05 conv: geometry not supported");
@@ -1128,6 +1155,10 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   TcParams& p = plan.p;
   p.has_addend = addend != nullptr ? 1 : 0;
   p.slope = slope;
+  p.epi_bn = epi_bn;
+  p.slope_res = slope_res;
+  DP_REQUIRE(!epi_bn || (part == nullptr && !bwd_stats && bn_ss != nullptr), DP_ERR_SHAPE,
+             "tcgen05 conv: the fused BatchNorm epilogue excludes statistics");
   p.dbg_skip = g_opt_dbg_skip;
   const CUtensorMapSwizzle sw = p.CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                            : (p.CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -1157,8 +1188,9 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
                        p.a_sb, dbox, p.st_layout);
   if (rc != DP_OK) return rc;
 
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
+  static std::mutex attr_mu;
+  static bool attr_done[DP_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
+  cudaError_t attr_err = cudaSuccess;
   typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const __nv_bfloat16*, float*,
                          long long*, const __nv_bfloat16*, const float*);
   static KernFn const kerns[20] = {tc_gather_gemm_kernel<0, 0, 1>, tc_gather_gemm_kernel<1, 1, 1>, tc_gather_gemm_kernel<2, 1, 1>,
@@ -1170,10 +1202,15 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
                                    tc_gather_gemm_kernel<1, 1, 2>, tc_gather_gemm_kernel<2, 1, 2>, tc_gather_gemm_kernel<3, 1, 2>,
                                    tc_gather_gemm_kernel<1, 0, 2>, tc_gather_gemm_kernel<2, 0, 2>, tc_gather_gemm_kernel<3, 0, 2>,
                                    tc_gather_gemm_kernel<4, 0, 2>};
-  std::call_once(attr_once, [] {
-    for (int i = 0; i < 20 && attr_err == cudaSuccess; ++i)
-      attr_err = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
-  });
+  {
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lk(attr_mu);
+    if (!attr_done[dev]) {
+      for (int i = 0; i < 20 && attr_err == cudaSuccess; ++i)
+        attr_err = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+      attr_done[dev] = attr_err == cudaSuccess;
+    }
+  }
   DP_REQUIRE(attr_err == cudaSuccess, DP_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s",
              cudaGetErrorString(attr_err));
   long long* dbg = (g_dbg && g_dbg_slots >= (size_t)148 * 16) ? g_dbg : nullptr;
@@ -1279,6 +1316,20 @@ int tc_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, fl
 
 bool tc_fwd_view_supported(const dp_conv_desc* d) { return tc_fwd_supported(d); }
 
+bool tc_fwd_bnact_supported(const dp_conv_desc* d) {
+  if (d->dtype != DP_BF16) return false;
+  TcPlan plan;
+  return plan_gather(fwd_problem(d), false, &plan);
+}
+
+// eval-mode Conv3dBlock in one kernel: z = lrelu(conv(x) * scale + shift, slope) [; z = lrelu(z + residual, slope_res)]
+int tc_conv_fwd_bnact(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* w, const float* scale_shift,
+                      float slope, const void* residual, float slope_res, void* z, cudaStream_t s) {
+  GatherProblem g = fwd_problem(d);
+  if (xstrides != nullptr) { g.ss_w = xstrides[0]; g.ss_h = xstrides[1]; g.ss_t = xstrides[2]; g.ss_b = xstrides[3]; }
+  return launch_gather(g, x, w, z, residual, nullptr, nullptr, s, nullptr, scale_shift, slope, 1, slope_res);
+}
+
 // stride-1 data gradient whose epilogue also produces the BatchNorm-backward sums of the layer that produced x
 bool tc_dgrad_bnstats_supported(const dp_conv_desc* d) {
   if (d->dtype != DP_BF16 || d->st != 1 || d->sh != 1 || d->sw != 1) return false;
@@ -1340,6 +1391,7 @@ int tc_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const vo
 DP_API int dp_set_option(const char* name, int value) {
   if (name == nullptr) return DP_ERR_SHAPE;
   if (!strcmp(name, "pdl")) { dp::g_pdl = value ? 1 : 0; return DP_OK; }
+  if (!strcmp(name, "strict_tc")) { dp::g_strict_tc = value ? 1 : 0; return DP_OK; }
   if (dp::tc_option(name, value, true) >= 0 || dp::wg_option(name, value, true) >= 0) return DP_OK;
   dp::set_error("dp_set_option: unknown option '%s'", name);
   return DP_ERR_UNSUPPORTED;
@@ -1347,6 +1399,7 @@ DP_API int dp_set_option(const char* name, int value) {
 DP_API int dp_get_option(const char* name) {
   if (name == nullptr) return -1;
   if (!strcmp(name, "pdl")) return dp::g_pdl;
+  if (!strcmp(name, "strict_tc")) return dp::g_strict_tc;
   const int v = dp::tc_option(name, 0, false);
   return v >= 0 ? v : dp::wg_option(name, 0, false);
 }

@@ -36,7 +36,9 @@ inline int check_launch(const char* what) {
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-int num_sms();
+constexpr int DP_MAX_DEVICES = 64;
+int current_device();   // clamped to [0, DP_MAX_DEVICES)
+int num_sms();          // of the current device
 
 // ---- programmatic dependent launch (PDL) ----
 // A step is ~370 short kernels; launched with programmatic stream serialization a kernel's CTAs may become resident

@@ -17,13 +17,19 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int num_sms() {
-  static int cached = 0;
-  if (cached) return cached;
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= DP_MAX_DEVICES) return 0;
+  return dev;
+}
+
+int num_sms() {   // per-device cache: one process may drive several GPUs
+  static int cached[DP_MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (cached[dev]) return cached[dev];
+  int n = 0;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
+  cached[dev] = n;
   return n;
 }
 

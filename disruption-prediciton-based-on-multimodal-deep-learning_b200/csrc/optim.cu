@@ -9,10 +9,12 @@ namespace dp {
 constexpr int OPT_THREADS = 256;
 constexpr int OPT_MAX_GRID = 1184;
 
+// Layout is part of the ABI (include/dp_b200.h): the host reads / restores `step` and `skipped` (checkpoints).
 struct OptWs {
   unsigned int counter;
   unsigned int step;      // device-side step count (used when the host passes step == 0: CUDA-graph replay)
-  unsigned int pad[2];
+  unsigned int skipped;   // steps skipped because the gradient norm was not finite (reference: train.py:55-60 `continue`)
+  unsigned int skip_now;  // 1 while the CURRENT step is being skipped (written by sqnorm, read by adamw)
   float partial[OPT_MAX_GRID];
 };
 
@@ -46,9 +48,15 @@ sqnorm_kernel(const float* __restrict__ g, int64_t n, float grad_scale, float* _
     __threadfence();
     double t = 0.0;
     for (unsigned int k = 0; k < gridDim.x; ++k) t += (double)*reinterpret_cast<volatile float*>(&ws->partial[k]);
-    norm_out[0] = (float)(sqrt(t) * (double)grad_scale);
+    const float nrm = (float)(sqrt(t) * (double)grad_scale);
+    norm_out[0] = nrm;
     ws->counter = 0u;
-    if (dev_step) ws->step += 1u;
+    // a non-finite loss gives non-finite gradients: the reference skips backward and step (train.py:55-60); here the
+    // whole update is skipped on the device (weights, moments and the step count stay untouched) and counted
+    const bool bad = !isfinite(nrm);
+    ws->skip_now = bad ? 1u : 0u;
+    if (bad) ws->skipped += 1u;
+    else if (dev_step) ws->step += 1u;
   }
 }
 
@@ -56,6 +64,7 @@ __global__ void __launch_bounds__(OPT_THREADS)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
              float max_norm, float grad_scale, const float* __restrict__ norm, const OptWs* __restrict__ ws, int dev_step) {
+  if (ws->skip_now) return;   // non-finite gradient norm: leave p, m, v as they are
   if (dev_step) {   // bias corrections from the device-side step count
     const float st = (float)ws->step;
     bc1 = 1.f - powf(beta1, st);
@@ -89,25 +98,39 @@ DP_API size_t dp_optim_workspace(int64_t n) {
   return sizeof(OptWs);
 }
 
-DP_API int dp_clip_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
-                              float beta2, float eps, float weight_decay, int step, float max_norm, float grad_scale,
-                              float* norm_out, void* workspace, void* stream) {
-  DP_REQUIRE(p && g && m && v && norm_out && workspace, DP_ERR_SHAPE, "dp_clip_adamw_step: NULL pointer");
-  DP_REQUIRE(n > 0 && step >= 0, DP_ERR_SHAPE, "dp_clip_adamw_step: n=%lld step=%d", (long long)n, step);
-  const int dev_step = step == 0 ? 1 : 0;   // step == 0: count steps on the device (CUDA-graph capturable)
-  DP_REQUIRE(((uintptr_t)g & 15) == 0, DP_ERR_ALIGN, "dp_clip_adamw_step: grad bucket must be 16-byte aligned");
-  cudaStream_t st = as_stream(stream);
+DP_API int dp_grad_sqnorm(const float* g, int64_t n, float grad_scale, int count_step, float* norm_out, void* workspace,
+                          void* stream) {
+  DP_REQUIRE(g && norm_out && workspace, DP_ERR_SHAPE, "dp_grad_sqnorm: NULL pointer");
+  DP_REQUIRE(n > 0, DP_ERR_SHAPE, "dp_grad_sqnorm: n=%lld", (long long)n);
+  DP_REQUIRE(((uintptr_t)g & 15) == 0, DP_ERR_ALIGN, "dp_grad_sqnorm: grad bucket must be 16-byte aligned");
   int64_t grid = (n / 4 + OPT_THREADS - 1) / OPT_THREADS;
   if (grid > OPT_MAX_GRID) grid = OPT_MAX_GRID;
   if (grid < 1) grid = 1;
-  sqnorm_kernel<<<(int)grid, OPT_THREADS, 0, st>>>(g, n, grad_scale, norm_out, (OptWs*)workspace, dev_step);
-  int rc = check_launch("dp_clip_adamw_step/sqnorm");
-  if (rc != DP_OK) return rc;
+  sqnorm_kernel<<<(int)grid, OPT_THREADS, 0, as_stream(stream)>>>(g, n, grad_scale, norm_out, (OptWs*)workspace, count_step ? 1 : 0);
+  return check_launch("dp_grad_sqnorm");
+}
+
+DP_API int dp_adamw_apply(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, int step, float max_norm, float grad_scale, const float* norm,
+                          const void* workspace, void* stream) {
+  DP_REQUIRE(p && g && m && v && norm && workspace, DP_ERR_SHAPE, "dp_adamw_apply: NULL pointer");
+  DP_REQUIRE(n > 0 && step >= 0, DP_ERR_SHAPE, "dp_adamw_apply: n=%lld step=%d", (long long)n, step);
+  const int dev_step = step == 0 ? 1 : 0;
   const float bc1 = 1.f - powf(beta1, (float)(step > 0 ? step : 1));
   const float bc2 = 1.f - powf(beta2, (float)(step > 0 ? step : 1));
   int64_t g2 = (n + OPT_THREADS - 1) / OPT_THREADS;
   if (g2 > OPT_MAX_GRID) g2 = OPT_MAX_GRID;
-  adamw_kernel<<<(int)g2, OPT_THREADS, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2),
-                                                max_norm, grad_scale, norm_out, (const OptWs*)workspace, dev_step);
-  return check_launch("dp_clip_adamw_step/adamw");
+  adamw_kernel<<<(int)g2, OPT_THREADS, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2),
+                                                max_norm, grad_scale, norm, (const OptWs*)workspace, dev_step);
+  return check_launch("dp_adamw_apply");
+}
+
+DP_API int dp_clip_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int step, float max_norm, float grad_scale,
+                              float* norm_out, void* workspace, void* stream) {
+  DP_REQUIRE(p && g && m && v && norm_out && workspace, DP_ERR_SHAPE, "dp_clip_adamw_step: NULL pointer");
+  int rc = dp_grad_sqnorm(g, n, grad_scale, step == 0, norm_out, workspace, stream);
+  if (rc != DP_OK) return rc;
+  return dp_adamw_apply(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, max_norm, grad_scale, norm_out, workspace,
+                        stream);
 }

@@ -151,6 +151,15 @@ DP_API int dp_stem_conv_fwd(const dp_conv_desc* d, const void* xp, const void* w
   return tc_conv_fwd_view(&v, xs, xp, wv, y, part, nparts, as_stream(stream));
 }
 
+DP_API int dp_stem_conv_fwd_bnact(const dp_conv_desc* d, const void* xp, const void* wv, const float* scale_shift, float slope,
+                                  void* z, void* stream) {
+  DP_REQUIRE(stem_ok(d), DP_ERR_UNSUPPORTED, "stem path: geometry not covered");
+  DP_REQUIRE(xp && wv && z && scale_shift, DP_ERR_SHAPE, "dp_stem_conv_fwd_bnact: NULL pointer");
+  long long xs[4];
+  dp_conv_desc v = stem_view(d, xs);
+  return tc_conv_fwd_bnact(&v, xs, xp, wv, scale_shift, slope, nullptr, 1.f, z, as_stream(stream));
+}
+
 DP_API size_t dp_stem_wgrad_workspace(const dp_conv_desc* d) {
   if (!stem_ok(d)) return 0;
   long long xs[4];

@@ -547,11 +547,17 @@ int tc_conv_wgrad_view(const dp_conv_desc* d, const long long* xstrides, const v
   const int ones[5] = {1, 1, 1, 1, 1};
   rc = wg_encode_map(&tmD, dy, d->Kp, d->Wo, d->Ho, d->To, d->B, plan.d_box, ones, p.cbD);
   if (rc != DP_OK) return rc;
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_MAX);
-  });
+  static std::mutex attr_mu;
+  static bool attr_done[DP_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
+  cudaError_t attr_err = cudaSuccess;
+  {
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lk(attr_mu);
+    if (!attr_done[dev]) {
+      attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_MAX);
+      attr_done[dev] = attr_err == cudaSuccess;
+    }
+  }
   DP_REQUIRE(attr_err == cudaSuccess, DP_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem): %s",
              cudaGetErrorString(attr_err));
   launch_pdl(wgrad_tc_kernel, dim3(plan.grid), dim3(WG_THREADS), plan.smem, s, tmX, tmD, p, (float*)ws,

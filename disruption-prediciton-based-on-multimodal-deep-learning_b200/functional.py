@@ -19,7 +19,7 @@ import torch
 
 from . import _lib as L
 
-_STATE = {"dtype": torch.bfloat16, "impl": L.IMPL_AUTO, "fuse_bn_reduce": True,
+_STATE = {"dtype": torch.bfloat16, "impl": L.IMPL_AUTO, "fuse_bn_reduce": True, "fuse_eval": True,
           # experiment, off: weight gradients on a second stream.  Measured 18.97 vs 19.02 ms/step: the wgrad CTAs cannot
           # co-reside with the 384-thread gather CTAs and the BatchNorm passes already fill the machine.
           "wgrad_stream": os.environ.get("DP_WGRAD_STREAM", "0") == "1"}
@@ -367,9 +367,13 @@ def _conv_fwd_call(lib, geom, x, wf, y, part, nparts, impl, st):
 
 
 def layer_forward(x, weight, gamma, beta, running_mean, running_var, cfg: LayerCfg, training: bool,
-                  residual=None, slope_res: float = 1.0, cache: Optional[PackedWeights] = None, geom=None):
+                  residual=None, slope_res: float = 1.0, cache: Optional[PackedWeights] = None, geom=None,
+                  fuse_eval: bool = False, x_view=None, x_ptr=None):
     """Returns (z, saved) with saved = (x, y, out_or_None, stats[4,Kp], w_dgrad, geom).
-    `geom` is given only by the stem fast path, where x is the packed-rows clip."""
+    `geom` is given only by the stem fast path, where x is the packed-rows clip.
+    `fuse_eval` (eval mode, no gradient needed): one kernel per layer (dp_conv_fwd_bnact), saved y is None.
+    `x_view` / `x_ptr` (fuse_eval only): element strides (w,h,t,b) and base address of an input VIEW inside `x`
+    (sliding windows over a per-frame cache); `geom` must then describe the view."""
     lib = L.load()
     st = L.stream_ptr()
     if geom is None:
@@ -393,7 +397,6 @@ def layer_forward(x, weight, gamma, beta, running_mean, running_var, cfg: LayerC
                                    stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
                                    st), "dp_bn_finalize")
     else:
-        L.check(_conv_fwd_call(lib, geom, x, wf, y, None, None, impl, st), "dp_conv_fwd")
         if running_mean is None or running_var is None:
             raise L.DpError("eval-mode BatchNorm needs running statistics")
         stats.zero_()
@@ -402,6 +405,24 @@ def layer_forward(x, weight, gamma, beta, running_mean, running_var, cfg: LayerC
         L.check(lib.dp_bn_eval_coeffs(running_mean.data_ptr(), running_var.data_ptr(), gamma.data_ptr(),
                                       beta.data_ptr(), cfg.eps, d.K, d.Kp, stats[2].data_ptr(), stats[3].data_ptr(),
                                       st), "dp_bn_eval_coeffs")
+        if fuse_eval and _STATE["fuse_eval"]:
+            # inference: BatchNorm (running statistics) + LeakyReLU [+ residual + LeakyReLU] in the conv epilogue; the raw
+            # conv output never reaches HBM and nothing is kept for a backward pass
+            if residual is not None and (residual.shape != y.shape or residual.dtype != y.dtype):
+                raise L.DpError(f"residual {tuple(residual.shape)} {residual.dtype} does not match {tuple(y.shape)} {y.dtype}")
+            t0 = _pb()
+            if geom.stem:
+                L.check(lib.dp_stem_conv_fwd_bnact(C.byref(d), x.data_ptr(), wf.data_ptr(), stats[2].data_ptr(), cfg.slope,
+                                                   y.data_ptr(), st), "dp_stem_conv_fwd_bnact")
+            else:
+                xs = (C.c_longlong * 4)(*x_view) if x_view is not None else None
+                L.check(lib.dp_conv_fwd_bnact(C.byref(d), xs, x.data_ptr() if x_ptr is None else x_ptr, wf.data_ptr(),
+                                              stats[2].data_ptr(), cfg.slope, _p(residual), float(slope_res), y.data_ptr(),
+                                              impl, st), "dp_conv_fwd_bnact")
+            if t0 is not None:
+                _pe(t0, geom.families(impl)[1], geom.flops, geom.esize * (geom.rows_in * d.C + geom.rows_out * d.K))
+            return y, (x, None, None, stats, wd, geom)
+        L.check(_conv_fwd_call(lib, geom, x, wf, y, None, None, impl, st), "dp_conv_fwd")
     z = torch.empty_like(y)
     if residual is not None and (residual.shape != y.shape or residual.dtype != y.dtype):
         raise L.DpError(f"residual {tuple(residual.shape)} {residual.dtype} does not match {tuple(y.shape)} {y.dtype}")
@@ -525,9 +546,11 @@ class ConvBnActFn(torch.autograd.Function):
         rm, rv = (mod.bn.running_mean, mod.bn.running_var) if mod.bn.track_running_stats else (None, None)
         if not training and rm is None:
             training = True
-        z, saved = layer_forward(x, weight, gamma, beta, rm, rv, mod._cfg, training, cache=mod._packed)
+        fused = not training and not any(ctx.needs_input_grad)
+        z, saved = layer_forward(x, weight, gamma, beta, rm, rv, mod._cfg, training, cache=mod._packed, fuse_eval=fused)
         xs, y, _, stats, wd, geom = saved
-        ctx.save_for_backward(xs, y, stats, wd)
+        if y is not None:
+            ctx.save_for_backward(xs, y, stats, wd)
         ctx.geom, ctx.cfg, ctx.training, ctx.wshape = geom, mod._cfg, training, weight.shape
         return z
 
@@ -553,10 +576,12 @@ class ConvBnActResFn(torch.autograd.Function):
         rm, rv = (mod.bn.running_mean, mod.bn.running_var) if mod.bn.track_running_stats else (None, None)
         if not training and rm is None:
             training = True
+        fused = not training and not any(ctx.needs_input_grad)
         z, saved = layer_forward(x, weight, gamma, beta, rm, rv, mod._cfg, training, residual=residual.contiguous(),
-                                 slope_res=slope_res, cache=mod._packed)
+                                 slope_res=slope_res, cache=mod._packed, fuse_eval=fused)
         xs, y, out, stats, wd, geom = saved
-        ctx.save_for_backward(xs, y, out, stats, wd)
+        if y is not None:
+            ctx.save_for_backward(xs, y, out, stats, wd)
         ctx.geom, ctx.cfg, ctx.training, ctx.wshape, ctx.slope_res = geom, mod._cfg, training, weight.shape, float(slope_res)
         return z
 
@@ -655,9 +680,12 @@ class StemConvBnActFn(torch.autograd.Function):
         rm, rv = (mod.bn.running_mean, mod.bn.running_var) if mod.bn.track_running_stats else (None, None)
         if not training and rm is None:
             training = True
-        z, saved = layer_forward(xp, weight, gamma, beta, rm, rv, mod._cfg, training, cache=mod._packed_stem, geom=geom)
+        fused = not training and not any(ctx.needs_input_grad)
+        z, saved = layer_forward(xp, weight, gamma, beta, rm, rv, mod._cfg, training, cache=mod._packed_stem, geom=geom,
+                                 fuse_eval=fused)
         _, y, _, stats, _, _ = saved
-        ctx.save_for_backward(xp, y, stats)
+        if y is not None:
+            ctx.save_for_backward(xp, y, stats)
         ctx.geom, ctx.cfg, ctx.training, ctx.wshape = geom, mod._cfg, training, weight.shape
         return z
 
@@ -721,13 +749,16 @@ class ResBlockFn(torch.autograd.Function):
         training = block.training
         saved_all = []
         metas = []
+        fused = not training and not any(ctx.needs_input_grad)
 
         def run(i, inp, residual=None, slope_res=1.0):
             m = layers[i]
             w, g, b = params[3 * i:3 * i + 3]
             z, saved = layer_forward(inp, w, g, b, m.bn.running_mean, m.bn.running_var, m._cfg, training,
-                                     residual=residual, slope_res=slope_res, cache=m._packed)
+                                     residual=residual, slope_res=slope_res, cache=m._packed, fuse_eval=fused)
             xs, y, out, stats, wd, geom = saved
+            if fused:
+                return z
             saved_all.extend([xs, y, stats, wd])
             metas.append((geom, m._cfg, w.shape))
             return z
@@ -741,6 +772,8 @@ class ResBlockFn(torch.autograd.Function):
         else:
             sc = x
         out = run(3, h, residual=sc, slope_res=block.relu.negative_slope)
+        if fused:
+            return out
         ctx.save_for_backward(out, *saved_all)
         ctx.metas, ctx.training, ctx.downsample = metas, training, block.downsample
         ctx.slope_res = float(block.relu.negative_slope)
@@ -820,6 +853,116 @@ class AvgPoolFn(torch.autograd.Function):
         L.check(L.load().dp_avgpool_bwd(g.data_ptr(), dx.data_ptr(), B, pixels, ctx.c, Cp, code, L.stream_ptr()),
                 "dp_avgpool_bwd")
         return dx, None
+
+
+# ----------------------------------------------------------------------------------------------
+# SlowFast auxiliaries (csrc/slowfast_ops.cu)
+# ----------------------------------------------------------------------------------------------
+class SeSwishFn(torch.autograd.Function):
+    """swish(x * gate[b, c]) on an internal tensor; gate = None gives the plain Swish
+    (reference resnet.py:63-81 SwishEfficient; the squeeze-excite scaling of Bottleneck3D.forward :186-192 fused in)."""
+
+    @staticmethod
+    def forward(ctx, x, gate, c):
+        B, Cp = x.shape[0], x.shape[-1]
+        pixels = x.numel() // (B * Cp)
+        x = x.contiguous()
+        g = None if gate is None else gate.contiguous().float()
+        out = torch.empty_like(x)
+        L.check(L.load().dp_se_swish_fwd(x.data_ptr(), _p(g), out.data_ptr(), B, pixels, c, Cp, _code(x), L.stream_ptr()),
+                "dp_se_swish_fwd")
+        ctx.save_for_backward(x, g)
+        ctx.c = c
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        x, g = ctx.saved_tensors
+        B, Cp = x.shape[0], x.shape[-1]
+        pixels = x.numel() // (B * Cp)
+        dout = dout.contiguous()
+        dx = torch.empty_like(x)
+        dgate = None if g is None else torch.empty((B, ctx.c), dtype=torch.float32, device=x.device)
+        L.check(L.load().dp_se_swish_bwd(x.data_ptr(), _p(g), dout.data_ptr(), dx.data_ptr(), _p(dgate), B, pixels, ctx.c, Cp,
+                                         _code(x), L.stream_ptr()), "dp_se_swish_bwd")
+        return dx, dgate, None
+
+
+def se_swish(x: torch.Tensor, gate: Optional[torch.Tensor]) -> torch.Tensor:
+    return tag(SeSwishFn.apply(x, gate, x._dp_c), x._dp_c)
+
+
+class MaxPoolHWFn(torch.autograd.Function):
+    """nn.MaxPool3d((1,3,3),(1,2,2),(0,1,1)) on an internal tensor (reference resnet.py:220-225)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, T, H, W, Cp = x.shape
+        x = x.contiguous()
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        out = torch.empty((B, T, Ho, Wo, Cp), dtype=x.dtype, device=x.device)
+        need_idx = any(ctx.needs_input_grad)
+        idx = torch.empty(out.shape, dtype=torch.uint8, device=x.device) if need_idx else None
+        L.check(L.load().dp_maxpool_hw_fwd(x.data_ptr(), out.data_ptr(), _p(idx), B * T, H, W, Cp, _code(x), L.stream_ptr()),
+                "dp_maxpool_hw_fwd")
+        if need_idx:
+            ctx.save_for_backward(idx)
+        ctx.shape, ctx.dtype = x.shape, x.dtype
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        B, T, H, W, Cp = ctx.shape
+        dout = dout.contiguous()
+        dx = torch.empty(ctx.shape, dtype=ctx.dtype, device=dout.device)
+        code = L.DP_BF16 if ctx.dtype == torch.bfloat16 else L.DP_F32
+        L.check(L.load().dp_maxpool_hw_bwd(dout.data_ptr(), idx.data_ptr(), dx.data_ptr(), B * T, H, W, Cp, code,
+                                           L.stream_ptr()), "dp_maxpool_hw_bwd")
+        return dx
+
+
+def maxpool_hw(x: torch.Tensor) -> torch.Tensor:
+    return tag(MaxPoolHWFn.apply(x), x._dp_c)
+
+
+class ConcatChannelsFn(torch.autograd.Function):
+    """torch.cat([a, b], dim=1) of the reference's NCDHW tensors (slowfast.py:26-36) on internal tensors."""
+
+    @staticmethod
+    def forward(ctx, a, b, ca, cb):
+        if a.shape[:-1] != b.shape[:-1] or a.dtype != b.dtype:
+            raise L.DpError(f"concat: {tuple(a.shape)} {a.dtype} vs {tuple(b.shape)} {b.dtype}")
+        a, b = a.contiguous(), b.contiguous()
+        cop = ceil16(ca + cb)
+        rows = a.numel() // a.shape[-1]
+        out = torch.empty((*a.shape[:-1], cop), dtype=a.dtype, device=a.device)
+        L.check(L.load().dp_concat_channels(a.data_ptr(), b.data_ptr(), out.data_ptr(), rows, ca, a.shape[-1], cb, b.shape[-1],
+                                            cop, _code(a), L.stream_ptr()), "dp_concat_channels")
+        ctx.meta = (a.shape, b.shape, ca, cb, cop, rows)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        sa, sb, ca, cb, cop, rows = ctx.meta
+        dout = dout.contiguous()
+        da = torch.empty(sa, dtype=dout.dtype, device=dout.device)
+        db = torch.empty(sb, dtype=dout.dtype, device=dout.device)
+        L.check(L.load().dp_split_channels(dout.data_ptr(), da.data_ptr(), db.data_ptr(), rows, ca, sa[-1], cb, sb[-1], cop,
+                                           _code(dout), L.stream_ptr()), "dp_split_channels")
+        return da, db, None, None
+
+
+def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    return tag(ConcatChannelsFn.apply(a, b, a._dp_c, b._dp_c), a._dp_c + b._dp_c)
+
+
+def global_avgpool(x: torch.Tensor) -> torch.Tensor:
+    """AdaptiveAvgPool3d(1) + flatten: internal tensor -> (B, C) fp32."""
+    return AvgPoolFn.apply(x, x._dp_c)
 
 
 # ----------------------------------------------------------------------------------------------

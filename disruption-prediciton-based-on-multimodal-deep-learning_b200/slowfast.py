@@ -9,8 +9,9 @@ initial weights) and the constructor's shape probe side effect on BatchNorm buff
 What runs where: every Conv3d (+ BatchNorm3d + ReLU, + fused residual add) -- 74 of them for layers [1,2,2,1] -- is
 the tcgen05 / CUDA-core conv family behind the C ABI, including the 3-channel stems (packed-rows fast path) and the
 stride-4 temporal lateral convs.  The glue between them (max-pool, squeeze-excite scaling with its two tiny fully
-connected layers, Swish, channel concatenation, temporal sub-sampling, global pool, MLP head) is plain PyTorch on
-the internal NDHWC tensors: it is < 1 % of the work and launch-bound either way (0.90 GFLOP/clip).
+connected layers on (B, C) vectors, temporal sub-sampling of the input clip, MLP head) is PyTorch; every pass over
+an activation tensor -- max-pool, squeeze-excite scaling fused with Swish, channel concatenation of the laterals,
+global pool -- is a kernel of csrc/slowfast_ops.cu / layout_pool.cu behind the C ABI, forward and backward.
 """
 from __future__ import annotations
 
@@ -84,25 +85,12 @@ class _ConvBN:
         return Fn.tag(z, self._cfg.K)
 
 
-def _logical(x: torch.Tensor) -> torch.Tensor:
-    """Internal (B,T,H,W,Cp) -> the logical channels (a view)."""
-    return x[..., : x._dp_c]
-
-
-def _repad(x: torch.Tensor, c: int) -> torch.Tensor:
-    """(B,T,H,W,c) -> internal tensor with channels zero-padded to a multiple of 16."""
-    cp = Fn.ceil16(c)
-    if cp != c:
-        x = F.pad(x, (0, cp - c))
-    return Fn.tag(x.contiguous(), c)
-
-
 class Swish(nn.Module):
-    """x * sigmoid(x) (reference resnet.py:63-81 hand-writes the backward; autograd gives the same derivative)."""
+    """x * sigmoid(x) (reference resnet.py:63-81 hand-writes the backward; csrc/slowfast_ops.cu does too)."""
 
     def forward(self, x):
         if Fn.is_internal(x):
-            return Fn.tag(x * torch.sigmoid(x), x._dp_c)
+            return Fn.se_swish(x, None)
         return x * torch.sigmoid(x)
 
 
@@ -154,14 +142,15 @@ class Bottleneck3D(nn.Module):
     def forward(self, x):
         x, was_internal = (x, True) if Fn.is_internal(x) else (Fn.to_internal(x), False)
         out = self._l2(self._l1(x))
-        if self.index % 2 == 0:      # squeeze-excite: global mean -> fc1 -> ReLU -> fc2 -> sigmoid -> channel scale
-            c = out._dp_c
-            o = _logical(out)
-            se = o.float().mean(dim=(1, 2, 3))
+        if self.index % 2 == 0:
+            # squeeze-excite: global mean (dp_avgpool_fwd) -> fc1 -> ReLU -> fc2 -> sigmoid on the (B, C) vector (two
+            # tiny fully connected layers, like the MLP head), then channel scale + Swish in ONE pass (dp_se_swish_fwd)
+            se = Fn.global_avgpool(out)
             se = F.relu(F.linear(se, self.fc1.weight.view(self.fc1.out_channels, -1), self.fc1.bias))
             se = torch.sigmoid(F.linear(se, self.fc2.weight.view(self.fc2.out_channels, -1), self.fc2.bias))
-            out = _repad(o * se.to(o.dtype)[:, None, None, None, :], c)
-        out = self.swish(out)
+            out = Fn.se_swish(out, se)
+        else:
+            out = self.swish(out)
         residual = self._ds(x) if self._ds is not None else x
         out = self._l3(out, residual=residual, slope_res=0.0)   # bn3(conv3) + residual -> ReLU, one fused layer
         return out if was_internal else Fn.to_ncdhw(out)
@@ -224,17 +213,18 @@ class ResNet3D(nn.Module):
     def _layer0(self, x):
         """conv(+bias) -> BN -> ReLU on the conv kernels (packed-rows stem for 3-channel clips), then the max-pool."""
         z = self._stem(x, stem_ok=True)
-        c = z._dp_c
-        p = self.layer0[3](z.permute(0, 4, 1, 2, 3))               # NCDHW view of the NDHWC tensor
-        return Fn.tag(p.permute(0, 2, 3, 4, 1).contiguous(), c)
+        mp = self.layer0[3]
+        if (_t3(mp.kernel_size), _t3(mp.stride), _t3(mp.padding)) != ((1, 3, 3), (1, 2, 2), (0, 1, 1)) or mp.ceil_mode:
+            raise NotImplementedError("dp_b200: only the reference's MaxPool3d((1,3,3),(1,2,2),(0,1,1)) is provided")
+        return Fn.maxpool_hw(z)
 
     @staticmethod
     def _pooled(x):
-        return _logical(x).float().mean(dim=(1, 2, 3))
+        return Fn.global_avgpool(x)
 
 
 def _cat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    return _repad(torch.cat([_logical(a), _logical(b)], dim=-1), a._dp_c + b._dp_c)
+    return Fn.concat_channels(a, b)
 
 
 class SlowNet(ResNet3D):

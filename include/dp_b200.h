@@ -72,6 +72,11 @@ int         dp_device_check(void);
 int         dp_num_sms(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long dp_launch_count(void);
+/* conv calls served by the CUDA-core (SIMT) family, and how many of those were DP_IMPL_AUTO falling back from
+ * tcgen05 on a bf16 tensor (a silent slow path: bench.py reports it and it must be 0 on the product path; the
+ * option "strict_tc" = 1 turns such a fallback into DP_ERR_UNSUPPORTED) */
+unsigned long long dp_simt_launch_count(void);
+unsigned long long dp_simt_fallback_count(void);
 /* tuning / debug switches: "tc_enable", "tc_halo", "tc_strided", "tc_max_stages", "tc_mma_stats", "tc_resident",
  * "wg_enable", "wg_halo", "wg_stack", "pdl" (programmatic dependent launch of the hot kernels) */
 int         dp_set_option(const char* name, int value);
@@ -94,11 +99,22 @@ int dp_u8_frames_to_ndhwc(const uint8_t* src, void* dst, const float* mean3, int
 int dp_pack_weights(const dp_conv_desc* d, const float* w, void* w_fwd, void* w_dgrad, void* stream);
 
 /* ---- convolution: forward / dgrad / wgrad (replace cuDNN behind nn.Conv3d, R2Plus1D.py:44-51,57) ---- */
-int dp_conv_supported(const dp_conv_desc* d, int op /*0 fwd,1 dgrad,2 wgrad,3 dgrad_bnstats fused in the epilogue*/, int impl);
+int dp_conv_supported(const dp_conv_desc* d, int op /*0 fwd,1 dgrad,2 wgrad,3 dgrad_bnstats fused in the epilogue,
+                                                      4 fwd_bnact fused in the epilogue*/, int impl);
 /* y = conv(x, w).  If `part` is non-NULL, per-channel (sum, sumsq) partials of y
  * are written to part[nparts][2][Kp] and *nparts is set (<= DP_MAX_PARTS). */
 int dp_conv_fwd(const dp_conv_desc* d, const void* x, const void* w_fwd, void* y,
                 float* part, int* nparts, int impl, void* stream);
+/* Eval-mode Conv3dBlock in ONE kernel (model.eval() at src/utils/utility.py:936-949, evaluate.py:38-44): BatchNorm
+ * with running statistics is the per-channel affine scale_shift = scale[Kp] ++ shift[Kp] (dp_bn_eval_coeffs), applied
+ * to the fp32 accumulator in the epilogue:  z = lrelu(conv(x,w)*scale + shift, slope); with `residual` (same shape
+ * as z; the tail of SpatioTemporalResBlock, R2Plus1D.py:181-187):  z = lrelu(z + residual, slope_res).  The raw conv
+ * output never reaches HBM.  `xstrides` (NULL = dense NDHWC) gives element strides of (w,h,t,b) of an input VIEW;
+ * overlapping views are allowed (sliding windows over a per-frame cache share frames: b and t strides both one
+ * frame), out-of-range coordinates of the view read as zero (= conv padding). */
+int dp_conv_fwd_bnact(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* w_fwd,
+                      const float* scale_shift, float slope, const void* residual, float slope_res, void* z,
+                      int impl, void* stream);
 /* dx = conv_transpose(dy, w) (+ addend if non-NULL, same shape as dx). */
 int dp_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend,
                   void* dx, int impl, void* stream);
@@ -128,6 +144,9 @@ int    dp_stem_pack_input_u8(const dp_conv_desc* d, const uint8_t* frames /* (B,
 int    dp_stem_pack_weights(const dp_conv_desc* d, const float* w, void* wv /* [Kp][kh][32] bf16 */, void* stream);
 int    dp_stem_conv_fwd(const dp_conv_desc* d, const void* xp, const void* wv, void* y, float* part, int* nparts,
                         void* stream);
+/* eval-mode stem: conv + BatchNorm(running statistics) + LeakyReLU in one kernel (see dp_conv_fwd_bnact) */
+int    dp_stem_conv_fwd_bnact(const dp_conv_desc* d, const void* xp, const void* wv, const float* scale_shift, float slope,
+                              void* z, void* stream);
 size_t dp_stem_wgrad_workspace(const dp_conv_desc* d);
 int    dp_stem_conv_wgrad(const dp_conv_desc* d, const void* xp, const void* dy, float* dw, void* workspace,
                           size_t workspace_bytes, void* stream);
@@ -167,6 +186,25 @@ int dp_avgpool_fwd(const void* x, float* out, int B, int64_t pixels, int C, int 
 int dp_avgpool_bwd(const float* dout, void* dx, int B, int64_t pixels, int C, int Cp, int dtype,
                    void* stream);
 
+/* ---- SlowFast auxiliaries (config 3; src/models/resnet.py:63-81,172-225, src/models/slowfast.py:26-36) ---- */
+/* out = swish(x * gate[b][c]) (gate NULL = plain Swish): the squeeze-excite scaling fused with SwishEfficient */
+int dp_se_swish_fwd(const void* x, const float* gate /* (B,C) or NULL */, void* out, int B, int64_t pixels, int C,
+                    int Cp, int dtype, void* stream);
+/* dx = dout * swish'(x*gate) * gate;  dgate[b][c] = sum_pixels dout * swish'(x*gate) * x  (NULL with gate NULL) */
+int dp_se_swish_bwd(const void* x, const float* gate, const void* dout, void* dx, float* dgate, int B,
+                    int64_t pixels, int C, int Cp, int dtype, void* stream);
+/* MaxPool3d(kernel (1,3,3), stride (1,2,2), padding (0,1,1)) over `frames` = B*T images of (H,W,Cp);
+ * idx (one byte per output element, may be NULL in inference) records the winning tap for the backward */
+int dp_maxpool_hw_fwd(const void* x, void* out, uint8_t* idx, int64_t frames, int H, int W, int Cp, int dtype,
+                      void* stream);
+int dp_maxpool_hw_bwd(const void* dout, const uint8_t* idx, void* dx, int64_t frames, int H, int W, int Cp,
+                      int dtype, void* stream);
+/* torch.cat([a, b], dim=channels) on channel-padded NDHWC rows (padding of the result zeroed), and its backward */
+int dp_concat_channels(const void* a, const void* b, void* out, int64_t rows, int Ca, int Cap, int Cb, int Cbp,
+                       int Cop, int dtype, void* stream);
+int dp_split_channels(const void* dout, void* da, void* db, int64_t rows, int Ca, int Cap, int Cb, int Cbp,
+                      int Cop, int dtype, void* stream);
+
 /* ---- losses (src/loss.py:14-81) ---- */
 size_t dp_loss_workspace(int64_t n);
 /* loss_out[0] = loss, loss_out[1] = normaliser (sum w[y] for LDAM, 1 otherwise).
@@ -178,8 +216,22 @@ int dp_loss_fwd_bwd(int kind, const float* logits, const int64_t* target, const 
 int dp_loss_bwd_scale(const float* dlogits, const float* grad_out, const float* loss_out,
                       float* out, int64_t count, void* stream);
 
-/* ---- fused optimiser tail (src/train.py:63-66: clip_grad_norm_ + AdamW.step) ---- */
+/* ---- fused optimiser tail (src/train.py:63-66: clip_grad_norm_ + AdamW.step) ----
+ * The workspace starts with four uint32 words the host may read / restore (checkpoints):
+ *   [0] internal counter, [1] step = number of updates applied, [2] skipped = steps skipped because the gradient
+ *   norm was not finite, [3] skip flag of the current step.
+ * A step whose (scaled) gradient norm is NaN/Inf is skipped ON THE DEVICE: weights, moments and the step count stay
+ * untouched -- the reference skips backward and step on a non-finite loss (src/train.py:55-60) -- with no host sync,
+ * so the guard also works inside a captured CUDA graph. */
 size_t dp_optim_workspace(int64_t n);
+/* the two halves of dp_clip_adamw_step: norm_out[0] = ||g * grad_scale||_2 (count_step != 0: the device step count
+ * advances if the norm is finite); then the AdamW update of one contiguous range (parameters without a gradient are
+ * left out of the ranges, as torch.optim.AdamW leaves them untouched). */
+int dp_grad_sqnorm(const float* g, int64_t n, float grad_scale, int count_step, float* norm_out, void* workspace,
+                   void* stream);
+int dp_adamw_apply(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int step, float max_norm, float grad_scale, const float* norm,
+                   const void* workspace, void* stream);
 /* flat fp32 param/grad/moment buffers of n elements; decoupled weight decay (AdamW).
  * max_norm <= 0 disables clipping.  grad_scale multiplies g first (1/world for DP mean).
  * step >= 1: bias-correction step given by the host; step == 0: the step count lives in `workspace` on the device
