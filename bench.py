@@ -3,6 +3,10 @@
 
     python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches it for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  # reference's CPU implementation on host cores
+    python bench.py --workload infer|slowfast|multimodal|loss   # configs 5 / 3 / 4 of BASELINE.json, loss-kernel sweep
+    python bench.py --caller stock                           # the UNCHANGED caller protocol of src/train.py:38-75
+    python bench.py --mode fp32                              # the fp32 validation mode (CUDA-core kernels)
+    python bench.py --check --gpus 2                         # multi-rank parity on real NCCL (bench_extra.py)
 
 One "step" = one pass of the hot path over one batch of synthetic clips:
     zero_grad -> forward (32 conv+BN+LeakyReLU layers, pool, head) -> Focal loss (DRW class weights)
@@ -42,31 +46,22 @@ TRAIN_GFLOP_PER_CLIP = 67.11   # fwd + dgrad + wgrad without the stem's unused d
 
 
 def measured_traffic(kernel_family: str):
-    """Average DRAM bytes per launch of the dominant kernel family from the committed `ncu --set full` capture
-    (profiles/*_prof_*_raw.csv, dram__bytes_read.sum + dram__bytes_write.sum); None if no capture is present."""
-    import csv
+    """Mean DRAM bytes per launch of a kernel family over ALL its launches of one training step, from the committed
+    ncu pass (profiles/*_dram_per_launch.json, written by scripts/summarize_dram.py from
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum`): the same set of launches the
+    algorithmic bytes per launch are averaged over.  (None, None) if no capture is present."""
     import glob
-    tag = {"tc_gather_gemm": "gather", "tc_wgrad": "wgrad"}.get(kernel_family, "bn")
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_prof_{tag}_raw.csv")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_dram_per_launch.json")))
     if not files:
         return None, None
-    rows = list(csv.reader(open(files[-1])))
-    if len(rows) < 3:
+    try:
+        d = json.load(open(files[-1]))
+        fam = d["families"].get(kernel_family)
+        if not fam:
+            return None, None
+        return fam["dram_bytes_per_launch"], f"{os.path.basename(files[-1])}: {fam['launches']} launches of one step"
+    except (OSError, ValueError, KeyError):
         return None, None
-    h, units = rows[0], rows[1]
-    unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot, n = 0.0, 0
-    for r in rows[2:]:
-        try:
-            v = 0.0
-            for col in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                i = h.index(col)
-                v += float(r[i]) * unit_scale.get(units[i], 1.0)
-            tot += v
-            n += 1
-        except (ValueError, IndexError):
-            continue
-    return (tot / n if n else None), os.path.basename(files[-1])
 
 
 def load_peaks():
@@ -224,14 +219,21 @@ def run_ours(args):
     model = R2Plus1DClassifier(CLIP, 2, LAYER_SIZES, False, alpha).to(dev).train()
     weights = dp_b200.drw_class_weights(40, 128, dp_b200.drw_betas(0.25), CLS_NUM)   # DRW epoch 40 of 128: beta=.25
     loss_fn = FocalLoss(weight=weights.to(dev), gamma=2.0)
-    opt = FusedClipAdamW(model.parameters(), lr=2e-4, max_norm=1.0, capturable=True)
+    stock = args.caller == "stock"
+    if stock:      # what an unmodified src/train.py gets: torch.optim.AdamW + clip_grad_norm_ + its three host syncs
+        opt = torch.optim.AdamW(model.parameters(), lr=2e-4)
+    else:
+        opt = FusedClipAdamW(model.parameters(), lr=2e-4, max_norm=1.0, capturable=True)
     reducer = None
     if world > 1:
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, src=0)
-        opt._ensure_flat(0, opt.param_groups[0])          # re-point params into the flat bucket first
-        reducer = dpd.BucketedGradAllReduce(model, average=False)
-        opt.grad_scale = 1.0 / world                      # DDP-mean semantics folded into the optimiser kernel
+        if stock:
+            reducer = dpd.BucketedGradAllReduce(model, average=True, time_collectives=True)
+        else:
+            # the reducer's buckets ARE contiguous slices of the optimiser's flat gradient buffer: no second buffer, no copy
+            reducer = dpd.BucketedGradAllReduce(model, average=False, optimizer=opt, time_collectives=True)
+            opt.grad_scale = 1.0 / world                  # DDP-mean semantics folded into the optimiser kernel
 
     # synthetic clips of the survey's distribution (uint8 grey levels minus BGR mean), seed 1234 + rank
     g = torch.Generator().manual_seed(1234 + rank)
@@ -254,6 +256,38 @@ def run_ours(args):
             opt.zero_grad(set_to_none=True)
         out = model(x)
         loss = loss_fn(out, y)
+        if stock:
+            # /root/reference/src/train.py:52-75 verbatim: isfinite (host sync 1), backward, clip, step, loss.item()
+            # (sync 2), argmax accuracy .item() (sync 3)
+            if not torch.isfinite(loss):
+                return loss
+            loss.backward()
+            if reducer is not None:
+                reducer.finish()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            step.train_loss += loss.item()
+            pred = torch.nn.functional.softmax(out, dim=1).max(1, keepdim=True)[1]
+            step.train_acc += pred.eq(y.view_as(pred)).sum().item()
+            return loss
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        opt.step()
+        return loss
+
+    step.train_loss, step.train_acc = 0.0, 0
+
+    MEAN = (90.0, 98.0, 102.0)
+
+    def step_u8(frames, y):
+        """The same step fed through the uint8 input boundary (n3): (B,T,H,W,3) uint8 BGR frames, mean subtraction and
+        layout change fused into the stem's input pack on the device (dataset.py:104-110,201-205)."""
+        if reducer is not None:
+            reducer.zero_grad()
+        else:
+            opt.zero_grad(set_to_none=True)
+        loss = loss_fn(model(frames, mean_bgr=MEAN), y)
         loss.backward()
         if reducer is not None:
             reducer.finish()
@@ -280,7 +314,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    with dp_b200.compute_mode("bf16", args.conv_impl):
+    use_graph = args.caller == "graph" and args.graph
+    u8 = args.e2e_input == "u8" and args.mode == "bf16" and not stock
+    with dp_b200.compute_mode(args.mode, args.conv_impl):
         # nvidia-smi takes a few hundred ms to produce its first sample: start it before the warm-up, report from mark()
         sampler = ClockSampler(local_rank)
         if rank == 0:
@@ -290,14 +326,24 @@ def run_ours(args):
             loss = step(x_dev[i % n_host], y_dev)
         barrier()
         assert torch.isfinite(loss).item(), "non-finite loss in warm-up"
-        if args.graph:
+        graphed_u8 = None
+        frames_host = frames_dev = None
+        if u8:      # the e2e leg ships uint8 frames: (B,T,H,W,3), 1.03 MB per clip instead of 4.13 MB
+            gq = torch.Generator().manual_seed(4321 + rank)
+            frames_host = [torch.randint(0, 256, (B, CLIP[1], CLIP[2], CLIP[3], 3), generator=gq, dtype=torch.uint8).pin_memory()
+                           for _ in range(n_host)]
+            frames_dev = frames_host[0].to(dev)
+            loss = step_u8(frames_dev, y_dev)
+        if use_graph:
             from dp_b200.graph import GraphedTrainStep
             loss = None      # drop the eager autograd graph (its AccumulateGrad nodes sit on the default stream)
+            kw = {}
             if reducer is not None:    # data parallel: bucket zeroing and the all-reduce waits are part of the graph
-                graphed = GraphedTrainStep(model, loss_fn, opt, x_dev[0], y_dev, warmup=1,
-                                           pre_backward=reducer.zero_grad, post_backward=reducer.finish)
-            else:
-                graphed = GraphedTrainStep(model, loss_fn, opt, x_dev[0], y_dev, warmup=1)
+                kw = dict(pre_backward=reducer.zero_grad, post_backward=reducer.finish)
+            graphed = GraphedTrainStep(model, loss_fn, opt, x_dev[0], y_dev, warmup=1, **kw)
+            if u8:
+                graphed_u8 = GraphedTrainStep(model, loss_fn, opt, frames_dev, y_dev, warmup=1,
+                                              forward=lambda f: model(f, mean_bgr=MEAN), **kw)
             for i in range(max(3, args.warmup)):
                 loss = run_step(x_dev[i % n_host], y_dev)
             barrier()
@@ -305,7 +351,7 @@ def run_ours(args):
 
         # ---- timed region A: inputs resident in HBM ----
         sampler.mark()
-        l0 = lib.dp_launch_count()
+        l0, sl0, sf0 = lib.dp_launch_count(), lib.dp_simt_launch_count(), lib.dp_simt_fallback_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -319,22 +365,30 @@ def run_ours(args):
 
         # ---- timed region B: end to end from pinned host memory (double-buffered H2D on a copy stream) ----
         e2e_steps = 0 if args.no_e2e else args.steps
+        src_host = frames_host if u8 else host
         copy_stream = torch.cuda.Stream(device=dev)
-        stage = [torch.empty_like(x_dev[0]) for _ in range(2)]
+        stage = [torch.empty_like(frames_dev if u8 else x_dev[0]) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
         ysrc = y_host.pin_memory()
+
+        def run_e2e_step(xb, yb):
+            if u8:
+                return graphed_u8.step(xb, yb)[0] if graphed_u8 is not None else step_u8(xb, yb)
+            return run_step(xb, yb)
 
         def issue_copy(i):
             s = i % 2
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[s])
-                stage[s].copy_(host[i % n_host], non_blocking=True)
+                stage[s].copy_(src_host[i % n_host], non_blocking=True)
                 ready[s].record(copy_stream)
 
         cur = torch.cuda.current_stream()
         for s in range(2):
             freed[s].record(cur)
+        for i in range(2 if e2e_steps else 0):     # the e2e graph's own warm-up (untimed)
+            run_e2e_step(frames_dev if u8 else x_dev[0], y_dev)
         barrier()
         t_e2e = []
         e0.record()
@@ -346,18 +400,29 @@ def run_ours(args):
                 issue_copy(i + 1)
             cur.wait_event(ready[s])
             yb = ysrc.to(dev, non_blocking=True)
-            loss = run_step(stage[s], yb)
+            loss = run_e2e_step(stage[s], yb)
             freed[s].record(cur)
             t_e2e.append(loss.item())                       # D2H read of the step's loss, every step
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
         clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions
-        h2d = host[0].numel() * 4 + ysrc.numel() * 8
+        h2d = src_host[0].numel() * src_host[0].element_size() + ysrc.numel() * 8
         d2h = 4
+        simt_launches = int(lib.dp_simt_launch_count() - sl0)
+        simt_fallbacks = int(lib.dp_simt_fallback_count() - sf0)
+
+        if args.nvtx_step:    # one extra EAGER step inside an NVTX range: `ncu --nvtx --nvtx-include "dp_step/"` sees exactly one step
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_push("dp_step")
+            step(x_dev[0], y_dev)
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_pop()
 
         # ---- per-kernel CUDA-event timing of the same step (roofline leg) ----
         kern = {}
+        if reducer is not None:
+            reducer.exposed_wait_ms()      # drop the events of the eager warm-up steps
         if rank == 0:
             Fn.PROFILER = Fn.KernelProfiler()
         for i in range(args.profile_steps):       # every rank steps (the step holds collectives); rank 0 records
@@ -365,6 +430,7 @@ def run_ours(args):
             # the per-kernel events then bracket GPU time, not host launch latency
             torch.cuda._sleep(int(6e7))
             step(x_dev[i % n_host], y_dev)
+        nccl_exposed_ms = reducer.exposed_wait_ms() if (reducer is not None and args.profile_steps) else None
         if rank == 0:
             kern = Fn.PROFILER.summary()
             if os.environ.get("DP_BENCH_DUMP"):     # per-launch list of the last profiled step (development aid)
@@ -401,6 +467,7 @@ def run_ours(args):
             peak = peaks["bf16_tflops_sustained"]
             roofline = {"kernel": top, "bound": "tensor", "achieved": r["tflops"], "peak": peak, "unit": "TFLOP/s",
                         "frac": round(r["tflops"] / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                        "traffic_over_algorithmic": None if not traffic else round(traffic / (kern[top]["bytes"] / kern[top]["launches"]), 3),
                         "algorithmic_bytes_per_launch": round(kern[top]["bytes"] / kern[top]["launches"], 1),
                         "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
                         "avg_launch_ms": round(r["ms_per_step"] / n_l, 4),
@@ -426,18 +493,25 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": f"R2Plus1DClassifier((3,21,128,128),2,[1,2,2,1],alpha={alpha}) train step: fwd + Focal(gamma=2, DRW "
-                               f"weights) + bwd + clip(1.0)+AdamW, batch {B}/GPU, bf16 storage / fp32 accumulate",
+                               f"weights) + bwd + clip(1.0)+AdamW, batch {B}/GPU, "
+                               + ("bf16 storage / fp32 accumulate" if args.mode == "bf16" else "fp32 validation mode (CUDA-core kernels)"),
                    "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": "inputs larger than L2 (264 MB of clips and >8 GB of activations per step vs 126 MB L2)",
                    "conv_impl": args.conv_impl, "final_loss": final_loss,
-                   "launch": "one CUDA graph replay per step" if graphed is not None else "eager (one Python call per kernel)"},
+                   "launch": "one CUDA graph replay per step" if graphed is not None else "eager (one Python call per kernel)",
+                   "caller": {"graph": "opt-in: FusedClipAdamW + GraphedTrainStep", "eager": "opt-in: FusedClipAdamW, eager launches",
+                              "stock": "unchanged caller (src/train.py:38-75): torch.optim.AdamW + clip_grad_norm_ + 3 host syncs per step"}[args.caller if (args.graph or args.caller != "graph") else "eager"]},
         "clocks": clocks,
         "e2e": None if args.no_e2e else {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 3),
-                "api": "model(x) / loss_fn / loss.backward() / optimizer.step() on fp32 NCDHW clips from pinned host memory"},
+                "api": ("model(frames_u8, mean_bgr) / loss_fn / loss.backward() / optimizer.step() on (B,T,H,W,3) uint8 frames from pinned "
+                        "host memory (mean subtraction + layout on the device)") if u8 else
+                       "model(x) / loss_fn / loss.backward() / optimizer.step() on fp32 NCDHW clips from pinned host memory"},
         "gpu_launches": launches,
+        "simt_launches": simt_launches, "simt_fallbacks": simt_fallbacks,
+        "nccl_exposed_ms_per_step": None if nccl_exposed_ms is None else round(nccl_exposed_ms, 4),
         "roofline": roofline,
         "kernels": fam_rows,
         "conv": {"ms_per_step": round(conv_ms, 3),
@@ -466,16 +540,34 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="issue every kernel from Python instead of replaying the captured step")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-memory leg (used for short ncu runs)")
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "slowfast", "multimodal", "loss"],
+                    help="train = BASELINE.json configs[1] (the headline); infer / slowfast / multimodal = configs 5 / 3 / 4; "
+                         "loss = the N = 2^24 sweep of the fused loss kernel")
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"], help="bf16 product mode or the fp32 validation mode")
+    ap.add_argument("--caller", default="graph", choices=["graph", "eager", "stock"],
+                    help="graph/eager: opt-in FusedClipAdamW (captured / eager); stock: the unchanged src/train.py step body")
+    ap.add_argument("--e2e-input", default="u8", choices=["u8", "f32"],
+                    help="what the end-to-end leg ships from pinned host memory: uint8 frames (n3 boundary) or fp32 NCDHW clips")
+    ap.add_argument("--nvtx-step", action="store_true", help="run one extra eager step inside the NVTX range 'dp_step' (ncu captures)")
+    ap.add_argument("--check", action="store_true", help="multi-rank parity check on real NCCL instead of a timing run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    if args.caller != "graph":
+        args.graph = False
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun (the driver launches torchrun itself)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    if args.check:
+        import bench_extra
+        return bench_extra.run_check(args)
+    if args.workload != "train":
+        import bench_extra
+        return getattr(bench_extra, "run_" + args.workload)(args)
     run_ours(args)
 
 

@@ -332,8 +332,10 @@ class R2Plus1DClassifier(nn.Module):
             x = self.res2plus1d(x)
         return x
 
-    def forward(self, x: torch.Tensor):
-        x = self.res2plus1d(x)
+    def forward(self, x: torch.Tensor, mean_bgr=None):
+        """x: (B,3,T,H,W) fp32 clips (the reference's call), or (B,T,H,W,3) uint8 BGR frames with `mean_bgr`
+        (the uint8 input boundary: mean subtraction and layout change run on the device, dataset.py:104-110)."""
+        x = self.res2plus1d(x, mean_bgr) if mean_bgr is not None else self.res2plus1d(x)
         x = self.linear(x)
         return x
 

@@ -24,13 +24,15 @@ from .optim import FusedClipAdamW
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, optimizer: FusedClipAdamW, example_x: torch.Tensor,
                  example_y: torch.Tensor, warmup: int = 3, pre_backward: Optional[Callable] = None,
-                 post_backward: Optional[Callable] = None):
+                 post_backward: Optional[Callable] = None, forward: Optional[Callable] = None):
         """`pre_backward` / `post_backward` run inside the captured step around `loss.backward()` (the data-parallel
-        trainer zeroes its gradient buckets / waits for the all-reduces there)."""
+        trainer zeroes its gradient buckets / waits for the all-reduces there).  `forward` replaces `model(x)` when the
+        batch is not what `model.forward` takes (uint8 frames + BGR mean: `lambda x: model(x, mean_bgr=MEAN)`)."""
         L.require_device()
         if not getattr(optimizer, "capturable", False):
             raise L.DpError("GraphedTrainStep needs FusedClipAdamW(capturable=True)")
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
+        self.forward = forward if forward is not None else model
         self.static_x = example_x.clone()
         self.static_y = example_y.clone()
         self.pre_backward, self.post_backward = pre_backward, post_backward
@@ -59,13 +61,14 @@ class GraphedTrainStep:
             self.pre_backward()
         else:
             self.optimizer.zero_grad(set_to_none=True)
-        out = self.model(self.static_x)
-        loss = self.loss_fn(out, self.static_y)
+        out = self.forward(self.static_x)
+        # a tuple of heads (the three-head GradientBlending model, train.py:46-50) goes to the loss unpacked
+        loss = self.loss_fn(*out, self.static_y) if isinstance(out, tuple) else self.loss_fn(out, self.static_y)
         loss.backward()
         if self.post_backward is not None:
             self.post_backward()
         self.optimizer.step()
-        return loss.detach(), out.detach()
+        return loss.detach(), (tuple(o.detach() for o in out) if isinstance(out, tuple) else out.detach())
 
     def step(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None):
         """Copy the batch into the static buffers (any device/pinned-host source, async) and replay.

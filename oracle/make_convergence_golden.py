@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--storage", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--heldout", type=int, default=64, help="held-out clips scored in eval mode after training")
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "convergence_ref.npz"))
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count() or 1)
@@ -77,7 +78,16 @@ def main():
         accs.append(float((logits.argmax(1) == y).float().mean()))
         if s % 10 == 0:
             print(f"step {s} loss {losses[-1]:.4f} acc {accs[-1]:.2f} ({time.time() - t0:.0f}s)", flush=True)
-    np.savez(args.out, loss=np.asarray(losses, np.float64), acc=np.asarray(accs, np.float64),
+    # held-out clips (steps >= 100000 of the same generator family), eval mode, final weights
+    held_logits = None
+    if args.storage == "fp32" and args.heldout > 0:
+        model.eval()
+        with torch.no_grad():
+            held_logits = torch.cat([model(task_batch(100000 + i, 16, 21, args.size, args.size)[0])
+                                     for i in range(args.heldout // 16)]).numpy()
+        held_y = torch.cat([task_batch(100000 + i, 16, 21, args.size, args.size)[1] for i in range(args.heldout // 16)]).numpy()
+    extra = {} if held_logits is None else {"heldout_logits": held_logits, "heldout_y": held_y}
+    np.savez(args.out, loss=np.asarray(losses, np.float64), acc=np.asarray(accs, np.float64), **extra,
              steps=args.steps, batch=args.batch, size=args.size, lr=LR, max_norm=MAX_NORM, alpha=ALPHA,
              storage=args.storage, source="reference" if args.storage == "fp32" else "port-bf16-storage")
     print("wrote", args.out)
