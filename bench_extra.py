@@ -261,22 +261,41 @@ def _train_harness(args, name, metric, build, make_batch, workload, flops_per_cl
     sampler = bench.ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    graphed = None
+
+    def run_step(batch):
+        if graphed is None:
+            return step(batch)
+        *xs, y = batch
+        return graphed.step(tuple(xs) if len(xs) > 1 else xs[0], y)[0]
+
     with dp_b200.compute_mode(args.mode, args.conv_impl):
         for i in range(max(3, args.warmup)):
             loss = step(dev_batches[i % 2])
         _sync(torch, dist, world)
         assert torch.isfinite(loss).item(), "non-finite loss in warm-up"
+        if args.graph:
+            from dp_b200.graph import GraphedTrainStep
+            loss = None
+            kw = dict(pre_backward=reducer.zero_grad, post_backward=reducer.finish) if reducer is not None else {}
+            *xs, y0 = dev_batches[0]
+            graphed = GraphedTrainStep(model, loss_fn, opt, tuple(xs) if len(xs) > 1 else xs[0], y0, warmup=1,
+                                       forward=lambda *a: forward(model, *a), **kw)
+            for i in range(max(3, args.warmup)):
+                loss = run_step(dev_batches[i % 2])
+            _sync(torch, dist, world)
+            assert torch.isfinite(loss).item(), "non-finite loss after graph capture"
         sampler.mark()
         l0, sl0, sf0 = lib.dp_launch_count(), lib.dp_simt_launch_count(), lib.dp_simt_fallback_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         _sync(torch, dist, world)
         e0.record()
         for i in range(args.steps):
-            loss = step(dev_batches[i % 2])
+            loss = run_step(dev_batches[i % 2])
         e1.record()
         _sync(torch, dist, world)
         ms_dev = _max_over_ranks(torch, dist, world, dev, e0.elapsed_time(e1))
-        launches = int(lib.dp_launch_count() - l0)
+        launches = int(lib.dp_launch_count() - l0) if graphed is None else graphed.launches_per_step * args.steps
         simt = int(lib.dp_simt_launch_count() - sl0)
         fallbacks = int(lib.dp_simt_fallback_count() - sf0)
         final_loss = float(loss.item())
@@ -284,8 +303,10 @@ def _train_harness(args, name, metric, build, make_batch, workload, flops_per_cl
         _sync(torch, dist, world)
         e0.record()
         for i in range(args.steps):
-            b = tuple(t.to(dev, non_blocking=True) for t in host_batches[i % 2])
-            step(b).item()
+            if graphed is not None:      # the replay's static buffers are filled straight from pinned host memory
+                run_step(host_batches[i % 2]).item()
+            else:
+                step(tuple(t.to(dev, non_blocking=True) for t in host_batches[i % 2])).item()
         e1.record()
         _sync(torch, dist, world)
         ms_e2e = _max_over_ranks(torch, dist, world, dev, e0.elapsed_time(e1))
@@ -331,7 +352,8 @@ def _train_harness(args, name, metric, build, make_batch, workload, flops_per_cl
         "warmup": max(3, args.warmup), "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single",
-                   "launch": "eager (one Python call per kernel)", "final_loss": final_loss,
+                   "launch": "one CUDA graph replay per step" if graphed is not None else "eager (one Python call per kernel)",
+                   "final_loss": final_loss,
                    "l2": "activations of one step exceed the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": round(clips / (ms_e2e / 1e3), 2), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -88,7 +88,9 @@ class TransformerEncoder(nn.Module):
         x = self.filter(self.noise(x).permute(0, 2, 1)).permute(2, 0, 1)          # (seq, batch, d)
         n = x.size(0)
         self.src_mask = torch.full((n, n), float("-inf"), device=x.device).triu(1)  # causal
-        x = self.transformer_encoder(self.pos_enc(x), self.src_mask).mean(dim=0)
+        # the mask IS the causal mask (reference transformer.py:105,111-114); saying so spares nn.TransformerEncoder its
+        # mask inspection, a host synchronisation per call that also forbids CUDA-graph capture of the step
+        x = self.transformer_encoder(self.pos_enc(x), self.src_mask, is_causal=True).mean(dim=0)
         return self.connector(x)
 
 

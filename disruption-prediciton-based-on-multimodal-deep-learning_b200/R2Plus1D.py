@@ -110,7 +110,7 @@ class Conv3dBlock(nn.Module):
         """External clip in, INTERNAL activation out (used by R2Plus1DNet for its first layer)."""
         self._refresh_cfg()
         xp = Fn.stem_pack_input(x, geom, mean_bgr)
-        z = Fn.StemConvBnActFn.apply(xp, self.conv.weight, self.bn.weight, self.bn.bias, self, geom)
+        z = Fn.stem_conv_bn_act(xp, self.conv.weight, self.bn.weight, self.bn.bias, self, geom)
         if self.training and self.bn.track_running_stats:
             self.bn.num_batches_tracked.add_(1)
         return Fn.tag(z, self._cfg.K)
@@ -118,7 +118,7 @@ class Conv3dBlock(nn.Module):
     def forward(self, x: torch.Tensor):
         x, was_internal = _enter(x)
         self._refresh_cfg()
-        z = Fn.ConvBnActFn.apply(x, self.conv.weight, self.bn.weight, self.bn.bias, self)
+        z = Fn.conv_bn_act(x, self.conv.weight, self.bn.weight, self.bn.bias, self)
         if self.training and self.bn.track_running_stats:
             self.bn.num_batches_tracked.add_(1)
         Fn.tag(z, self._cfg.K)
@@ -200,7 +200,7 @@ class SpatioTemporalResBlock(nn.Module):
             for m in layers:
                 m._refresh_cfg()
                 params += [m.conv.weight, m.bn.weight, m.bn.bias]
-            out = Fn.ResBlockFn.apply(x, self, *params)
+            out = Fn.res_block(x, self, *params)
             if self.training:
                 for m in layers:
                     if m.bn.track_running_stats:

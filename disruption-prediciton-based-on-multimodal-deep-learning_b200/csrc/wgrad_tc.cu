@@ -515,16 +515,34 @@ static int wg_encode_map(CUtensorMap* m, const void* ptr, int C, int W, int H, i
   return DP_OK;
 }
 
+// Output-channel halves: when neither operand order fits one N tile (both channel counts > 256: the 320 -> 512 shortcut
+// of SlowFast's last stage), the weight gradient is computed as two problems over halves of K -- dy read through a
+// strided view, dw rows [0, K/2) and [K/2, K) are contiguous blocks of the (K, C, taps) master layout.
+static bool split_halves(const dp_conv_desc* d, dp_conv_desc* h0, dp_conv_desc* h1) {
+  if (d->Kp <= 256 || d->Kp % 32) return false;
+  const int half = d->Kp / 2;
+  if (d->K <= half) return false;
+  *h0 = *d; *h1 = *d;
+  h0->Kp = half; h0->K = half;
+  h1->Kp = half; h1->K = d->K - half;
+  return true;
+}
+
 bool tc_wgrad_supported(const dp_conv_desc* d) {
   if (d->dtype != DP_BF16) return false;
   WgPlan plan;
-  return plan_wgrad(d, &plan);
+  if (plan_wgrad(d, &plan)) return true;
+  dp_conv_desc h0, h1;
+  return split_halves(d, &h0, &h1) && plan_wgrad(&h0, &plan);
 }
 
 size_t tc_wgrad_workspace(const dp_conv_desc* d) {
   WgPlan plan;
-  if (!plan_wgrad(d, &plan)) return 0;
-  return (size_t)plan.p.nsplit * d->Kp * plan.p.taps * d->Cp * sizeof(float);
+  if (plan_wgrad(d, &plan)) return (size_t)plan.p.nsplit * d->Kp * plan.p.taps * d->Cp * sizeof(float);
+  dp_conv_desc h0, h1;
+  if (split_halves(d, &h0, &h1) && plan_wgrad(&h0, &plan))
+    return (size_t)plan.p.nsplit * h0.Kp * plan.p.taps * d->Cp * sizeof(float);
+  return 0;
 }
 
 int tc_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
@@ -532,8 +550,29 @@ int tc_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* d
   return tc_conv_wgrad_view(d, nullptr, x, dy, dw, ws, ws_bytes, s);
 }
 
+static int wgrad_launch(const dp_conv_desc* d, const long long* xstrides, const void* x, const long long* dystrides,
+                        const void* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t s);
+
 int tc_conv_wgrad_view(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* dy, float* dw,
                        void* ws, size_t ws_bytes, cudaStream_t s) {
+  WgPlan plan;
+  if (plan_wgrad(d, &plan)) return wgrad_launch(d, xstrides, x, nullptr, dy, dw, ws, ws_bytes, s);
+  dp_conv_desc h[2];
+  DP_REQUIRE(split_halves(d, &h[0], &h[1]) && plan_wgrad(&h[0], &plan), DP_ERR_UNSUPPORTED,
+             "tcgen05 wgrad: geometry not supported");
+  const long long dys[4] = {(long long)d->Kp, (long long)d->Wo * d->Kp, (long long)d->Ho * d->Wo * d->Kp,
+                            (long long)d->To * d->Ho * d->Wo * d->Kp};
+  const int taps = d->kt * d->kh * d->kw;
+  for (int i = 0; i < 2; ++i) {
+    const int rc = wgrad_launch(&h[i], xstrides, x, dys, (const __nv_bfloat16*)dy + i * h[0].Kp,
+                                dw + (size_t)i * h[0].Kp * d->C * taps, ws, ws_bytes, s);
+    if (rc != DP_OK) return rc;
+  }
+  return DP_OK;
+}
+
+static int wgrad_launch(const dp_conv_desc* d, const long long* xstrides, const void* x, const long long* dystrides,
+                        const void* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t s) {
   WgPlan plan;
   DP_REQUIRE(plan_wgrad(d, &plan), DP_ERR_UNSUPPORTED, "tcgen05 wgrad: geometry not supported");
   DP_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)ws & 15) == 0, DP_ERR_ALIGN,
@@ -545,7 +584,7 @@ int tc_conv_wgrad_view(const dp_conv_desc* d, const long long* xstrides, const v
   int rc = wg_encode_map(&tmX, x, d->Cp, d->Wi, d->Hi, d->Ti, d->B, plan.x_box, plan.x_estride, p.cbX, xstrides);
   if (rc != DP_OK) return rc;
   const int ones[5] = {1, 1, 1, 1, 1};
-  rc = wg_encode_map(&tmD, dy, d->Kp, d->Wo, d->Ho, d->To, d->B, plan.d_box, ones, p.cbD);
+  rc = wg_encode_map(&tmD, dy, d->Kp, d->Wo, d->Ho, d->To, d->B, plan.d_box, ones, p.cbD, dystrides);
   if (rc != DP_OK) return rc;
   static std::mutex attr_mu;
   static bool attr_done[DP_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device

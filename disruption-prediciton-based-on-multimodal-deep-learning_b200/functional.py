@@ -23,6 +23,7 @@ _STATE = {"dtype": torch.bfloat16, "impl": L.IMPL_AUTO, "fuse_bn_reduce": True, 
           # experiment, off: weight gradients on a second stream.  Measured 18.97 vs 19.02 ms/step: the wgrad CTAs cannot
           # co-reside with the 384-thread gather CTAs and the BatchNorm passes already fill the machine.
           "wgrad_stream": os.environ.get("DP_WGRAD_STREAM", "0") == "1"}
+_GRAD = [True]  # autograd mode of the CALLER of the layer functions (inside Function.forward it is always off)
 _SIDE = {}
 _PENDING = []   # (done event, tensors kept alive until the main stream has waited for it)
 
@@ -546,7 +547,7 @@ class ConvBnActFn(torch.autograd.Function):
         rm, rv = (mod.bn.running_mean, mod.bn.running_var) if mod.bn.track_running_stats else (None, None)
         if not training and rm is None:
             training = True
-        fused = not training and not any(ctx.needs_input_grad)
+        fused = not training and (not _GRAD[0] or not any(ctx.needs_input_grad))
         z, saved = layer_forward(x, weight, gamma, beta, rm, rv, mod._cfg, training, cache=mod._packed, fuse_eval=fused)
         xs, y, _, stats, wd, geom = saved
         if y is not None:
@@ -576,7 +577,7 @@ class ConvBnActResFn(torch.autograd.Function):
         rm, rv = (mod.bn.running_mean, mod.bn.running_var) if mod.bn.track_running_stats else (None, None)
         if not training and rm is None:
             training = True
-        fused = not training and not any(ctx.needs_input_grad)
+        fused = not training and (not _GRAD[0] or not any(ctx.needs_input_grad))
         z, saved = layer_forward(x, weight, gamma, beta, rm, rv, mod._cfg, training, residual=residual.contiguous(),
                                  slope_res=slope_res, cache=mod._packed, fuse_eval=fused)
         xs, y, out, stats, wd, geom = saved
@@ -680,7 +681,7 @@ class StemConvBnActFn(torch.autograd.Function):
         rm, rv = (mod.bn.running_mean, mod.bn.running_var) if mod.bn.track_running_stats else (None, None)
         if not training and rm is None:
             training = True
-        fused = not training and not any(ctx.needs_input_grad)
+        fused = not training and (not _GRAD[0] or not any(ctx.needs_input_grad))
         z, saved = layer_forward(xp, weight, gamma, beta, rm, rv, mod._cfg, training, cache=mod._packed_stem, geom=geom,
                                  fuse_eval=fused)
         _, y, _, stats, _, _ = saved
@@ -749,7 +750,7 @@ class ResBlockFn(torch.autograd.Function):
         training = block.training
         saved_all = []
         metas = []
-        fused = not training and not any(ctx.needs_input_grad)
+        fused = not training and (not _GRAD[0] or not any(ctx.needs_input_grad))
 
         def run(i, inp, residual=None, slope_res=1.0):
             m = layers[i]
@@ -826,6 +827,25 @@ class ResBlockFn(torch.autograd.Function):
             flat.extend(grads[i])
         join_side_stream()
         return (dx, None, *flat)
+
+
+def _caller(fn):
+    """Entry point of a layer Function for module code: records whether the CALLER runs under autograd (inside
+    Function.forward grad mode is always off, and `needs_input_grad` is True for parameters even under no_grad), so
+    eval-mode inference takes the fused conv + BatchNorm + activation kernels."""
+    def call(*args):
+        _GRAD[0] = torch.is_grad_enabled()
+        try:
+            return fn.apply(*args)
+        finally:
+            _GRAD[0] = True
+    return call
+
+
+conv_bn_act = _caller(ConvBnActFn)
+conv_bn_act_res = _caller(ConvBnActResFn)
+stem_conv_bn_act = _caller(StemConvBnActFn)
+res_block = _caller(ResBlockFn)
 
 
 class AvgPoolFn(torch.autograd.Function):

@@ -33,7 +33,9 @@ class GraphedTrainStep:
             raise L.DpError("GraphedTrainStep needs FusedClipAdamW(capturable=True)")
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
         self.forward = forward if forward is not None else model
-        self.static_x = example_x.clone()
+        # several input tensors (video clip + 0D signals of the multimodal model) are passed as a tuple
+        self._multi = isinstance(example_x, (tuple, list))
+        self.static_x = tuple(t.clone() for t in example_x) if self._multi else example_x.clone()
         self.static_y = example_y.clone()
         self.pre_backward, self.post_backward = pre_backward, post_backward
         # AccumulateGrad nodes created by earlier eager steps live on the default stream for as long as any tensor
@@ -41,7 +43,7 @@ class GraphedTrainStep:
         # the caller must drop such references; collect what is already unreachable
         import gc
         gc.collect()
-        side = torch.cuda.Stream(device=example_x.device)
+        side = torch.cuda.Stream(device=example_y.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):          # allocator, workspaces, weight packs, kernel attributes settle
@@ -61,7 +63,7 @@ class GraphedTrainStep:
             self.pre_backward()
         else:
             self.optimizer.zero_grad(set_to_none=True)
-        out = self.forward(self.static_x)
+        out = self.forward(*self.static_x) if self._multi else self.forward(self.static_x)
         # a tuple of heads (the three-head GradientBlending model, train.py:46-50) goes to the loss unpacked
         loss = self.loss_fn(*out, self.static_y) if isinstance(out, tuple) else self.loss_fn(out, self.static_y)
         loss.backward()
@@ -73,7 +75,10 @@ class GraphedTrainStep:
     def step(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None):
         """Copy the batch into the static buffers (any device/pinned-host source, async) and replay.
         Returns (loss, logits) as static device tensors valid until the next step."""
-        if x is not None:
+        if x is not None and self._multi:
+            for dst, src in zip(self.static_x, x):
+                dst.copy_(src, non_blocking=True)
+        elif x is not None:
             self.static_x.copy_(x, non_blocking=True)
         if y is not None:
             self.static_y.copy_(y, non_blocking=True)

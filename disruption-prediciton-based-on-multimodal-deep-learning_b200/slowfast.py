@@ -71,13 +71,13 @@ class _ConvBN:
                     geom = Fn.stem_geom(self._cfg, x.shape[0], x.shape[2], x.shape[3], x.shape[4])
                 if geom is not None:
                     xp = Fn.stem_pack_input(x, geom)
-                    z = Fn.StemConvBnActFn.apply(xp, self.conv.weight, bn.weight, bn.bias, self, geom)
+                    z = Fn.stem_conv_bn_act(xp, self.conv.weight, bn.weight, bn.bias, self, geom)
                 else:
-                    z = Fn.ConvBnActFn.apply(Fn.to_internal(x), self.conv.weight, bn.weight, bn.bias, self)
+                    z = Fn.conv_bn_act(Fn.to_internal(x), self.conv.weight, bn.weight, bn.bias, self)
             elif residual is not None:
-                z = Fn.ConvBnActResFn.apply(x, self.conv.weight, bn.weight, bn.bias, residual, self, float(slope_res))
+                z = Fn.conv_bn_act_res(x, self.conv.weight, bn.weight, bn.bias, residual, self, float(slope_res))
             else:
-                z = Fn.ConvBnActFn.apply(x, self.conv.weight, bn.weight, bn.bias, self)
+                z = Fn.conv_bn_act(x, self.conv.weight, bn.weight, bn.bias, self)
         finally:
             self._bias_fixups(before=False)
         if self.training and bn.track_running_stats:

@@ -255,3 +255,21 @@ def test_every_layer_of_the_benchmark_has_a_tcgen05_plan():
             if not lib.dp_conv_supported(C.byref(d), op, L.IMPL_TC):
                 missing.append((name, what))
     assert not missing, missing
+
+
+def test_every_slowfast_conv_has_a_tcgen05_plan(golden_dir):
+    """All 74 convolutions of SlowFast [1,2,2,1] at the config-3 clip (geometries recorded from the reference by
+    oracle/make_golden_r2.py) have tcgen05 plans for forward, data gradient and weight gradient at batch 2 and 64: the
+    bf16 path never drops to the CUDA-core family.  Host-side planner only: runs on the CPU."""
+    import ctypes as C
+    import json
+    from dp_b200 import _lib as L, functional as Fn
+    lib = L.load()
+    geoms = json.load(open(os.path.join(golden_dir, "slowfast_conv_geoms.json")))
+    assert len(geoms) == 74
+    for B in (2, 64):
+        for g in geoms:
+            cg = Fn.ConvGeom(g["C"], g["K"], tuple(g["kernel"]), tuple(g["stride"]), tuple(g["padding"]), B, g["T"], g["H"], g["W"],
+                             L.DP_BF16)
+            for op in range(3):
+                assert lib.dp_conv_supported(C.byref(cg.desc), op, L.IMPL_TC), (B, g, op)

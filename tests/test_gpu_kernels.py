@@ -51,6 +51,7 @@ GEOMS = [
     (230, 128, (3, 1, 1), (2, 1, 1), (1, 0, 0), 3, 4, 4),     # conv5 down temporal
     (128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 4, 4),     # conv5 spatial (N > 256)
     (288, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0), 2, 4, 4),     # conv5 temporal
+    (320, 512, (1, 1, 1), (1, 2, 2), (0, 0, 0), 5, 8, 8),     # SlowFast layer4 shortcut: both channel counts > 256 (wgrad in K halves)
 ]
 # full-resolution shapes for the tensor-core family (tile edges, halo boxes, 64-wide rows)
 GEOMS_BIG = [
