@@ -140,12 +140,13 @@ class BucketedGradAllReduce:
                 if left > 0:  # parameters that received no gradient this step
                     self._works.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group,
                                                        async_op=True))
-            if self.time_collectives and torch.cuda.is_available():
+            timed = self.time_collectives and torch.cuda.is_available() and not torch.cuda.is_current_stream_capturing()
+            if timed:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record()
             for w in self._works:
                 w.wait()
-            if self.time_collectives and torch.cuda.is_available():
+            if timed:
                 e1 = torch.cuda.Event(enable_timing=True)
                 e1.record()
                 self._wait_events.append((e0, e1))
