@@ -79,8 +79,9 @@ def run_infer(args):
     n_win = inference.num_windows(n_frames, seq_len, dgap)          # 1000
     rng = dpd.shard_range(n_win, rank, world)
 
-    def one_pass(fr, bs, cache=True):
-        return inference.sliding_window_probs(model, fr, seq_len, dgap, batch_size=bs, window_range=rng, stem_cache=cache)
+    def one_pass(fr, bs, cache=True, graph=True):
+        return inference.sliding_window_probs(model, fr, seq_len, dgap, batch_size=bs, window_range=rng, stem_cache=cache,
+                                              use_graph=graph)
 
     sweep = {}
     sampler = bench.ClockSampler(local_rank)
@@ -108,6 +109,14 @@ def run_infer(args):
             ms = _max_over_ranks(torch, dist, world, dev, e0.elapsed_time(e1)) / reps
             sweep[bs] = {"windows_per_s": round(n_win / (ms / 1e3), 1), "ms_per_shot": round(ms, 3),
                          "launches_per_shot": int((lib.dp_launch_count() - l0) // reps)}
+        # batch 1 with every kernel issued from Python (no CUDA-graph replay): the launch-bound regime of the reference loop
+        one_pass(frames, 1, graph=False)
+        _sync(torch, dist, world)
+        e0.record()
+        one_pass(frames, 1, graph=False)
+        e1.record()
+        _sync(torch, dist, world)
+        ms_b1_eager = _max_over_ranks(torch, dist, world, dev, e0.elapsed_time(e1))
         # without the per-frame stem cache (what batching alone buys)
         for _ in range(2):
             one_pass(frames, 256, cache=False)
@@ -142,7 +151,7 @@ def run_infer(args):
         if rank == 0:
             Fn.PROFILER = Fn.KernelProfiler()
             torch.cuda._sleep(int(6e7))
-            one_pass(frames, 256)
+            one_pass(frames, 256, graph=False)
             kern = Fn.PROFILER.summary()
             Fn.PROFILER = None
         clocks = sampler.stop() if rank == 0 else None
@@ -173,6 +182,7 @@ def run_infer(args):
         "config": {"workload": "config 5: sliding-window inference (utility.py:896-977) over a synthetic 1024-frame uint8 shot, seq_len 21, "
                                "dist 3 -> 1000 windows, eval mode; one step = the whole shot; windows sharded over ranks, no collective",
                    "batch_sweep": {str(k): v for k, v in sweep.items()}, "value_is": "batch 256 per GPU",
+                   "batch1_without_graph_replay": {"windows_per_s": round(n_win / (ms_b1_eager / 1e3), 1), "ms_per_shot": round(ms_b1_eager, 3)},
                    "without_stem_frame_cache": {"windows_per_s": round(n_win / (ms_nocache / 1e3), 1), "ms_per_shot": round(ms_nocache, 3)},
                    "batch1_latency_s": {"mean": round(float(np.mean(lat)), 5), "std": round(float(np.std(lat)), 5), "samples": len(lat),
                                         "how": "model(x) on a (1,3,21,128,128) fp32 clip + .cpu(), time.time(), as measure_computation_time "

@@ -56,6 +56,9 @@ SIGNATURES = {
     "dp_conv_fwd": (_i, [_pdesc, _vp, _vp, _vp, _vp, _pint, _i, _vp]),
     "dp_conv_fwd_bnact": (_i, [_pdesc, C.POINTER(C.c_longlong), _vp, _vp, _vp, _f, _vp, _f, _vp, _i, _vp]),
     "dp_conv_dgrad": (_i, [_pdesc, _vp, _vp, _vp, _vp, _i, _vp]),
+    "dp_dgrad_classes_weight_elems": (_sz, [_pdesc, _i]),
+    "dp_pack_weights_dgrad_classes": (_i, [_pdesc, _vp, _vp, _vp]),
+    "dp_conv_dgrad_classes": (_i, [_pdesc, _vp, _vp, _vp, _vp, _vp]),
     "dp_conv_dgrad_bnstats": (_i, [_pdesc, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _pint, _i, _vp]),
     "dp_conv_wgrad_workspace": (_sz, [_pdesc, _i]),
     "dp_conv_wgrad": (_i, [_pdesc, _vp, _vp, _vp, _vp, _sz, _i, _vp]),

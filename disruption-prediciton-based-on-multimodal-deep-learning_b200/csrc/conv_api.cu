@@ -155,6 +155,26 @@ DP_API int dp_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w_dg
   return simt_conv_dgrad(d, dy, w_dgrad, addend, dx, s);
 }
 
+DP_API size_t dp_dgrad_classes_weight_elems(const dp_conv_desc* d, int impl) {
+  if (validate(d) != DP_OK || impl == DP_IMPL_SIMT) return 0;
+  return tc_dgrad_classes_weight_elems(d);
+}
+
+DP_API int dp_pack_weights_dgrad_classes(const dp_conv_desc* d, const float* w, void* w_cls, void* stream) {
+  int rc = validate(d);
+  if (rc != DP_OK) return rc;
+  DP_REQUIRE(w && w_cls, DP_ERR_SHAPE, "dp_pack_weights_dgrad_classes: NULL pointer");
+  return tc_pack_dgrad_classes(d, w, w_cls, as_stream(stream));
+}
+
+DP_API int dp_conv_dgrad_classes(const dp_conv_desc* d, const void* dy, const void* w_cls, const void* addend, void* dx,
+                                 void* stream) {
+  int rc = validate(d);
+  if (rc != DP_OK) return rc;
+  DP_REQUIRE(dy && w_cls && dx, DP_ERR_SHAPE, "dp_conv_dgrad_classes: NULL pointer");
+  return tc_conv_dgrad_classes(d, dy, w_cls, addend, dx, as_stream(stream));
+}
+
 DP_API int dp_conv_dgrad_bnstats(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx,
                                  const void* y_prev, const float* scale_shift, float slope, float* part, int* nparts,
                                  int impl, void* stream) {

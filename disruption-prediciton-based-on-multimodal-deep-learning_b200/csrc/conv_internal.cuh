@@ -32,6 +32,10 @@ bool tc_dgrad_bnstats_supported(const dp_conv_desc* d);
 int tc_conv_dgrad_bnstats(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
                           const void* yprev, const float* bn_scale_shift, float slope, float* part, int* nparts,
                           cudaStream_t s);
+// strided data gradient with every stride-parity class in one launch (class-packed weights, see conv_tc.cu)
+size_t tc_dgrad_classes_weight_elems(const dp_conv_desc* d);   // 0: not supported for this geometry
+int tc_pack_dgrad_classes(const dp_conv_desc* d, const float* w, void* out, cudaStream_t s);
+int tc_conv_dgrad_classes(const dp_conv_desc* d, const void* dy, const void* w_cls, const void* addend, void* dx, cudaStream_t s);
 size_t tc_wgrad_workspace(const dp_conv_desc* d);
 int tc_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t s);

@@ -71,6 +71,12 @@ struct TcParams {
   //   v = lrelu(acc * scale[c] + shift[c], slope);  with an addend (the residual):  v = lrelu(v + addend, slope_res)
   int epi_bn;
   float slope_res;
+  // stride-parity classes of a strided data gradient in ONE launch (STATS == 0): destination column g = n * Ntile + c
+  // belongs to class g / cpd, channel g % cpd; each class is written through its own strided view (tmD, tmD1..3) and reads
+  // its own addend origin / extent.  ncls <= 1: plain destination
+  int ncls, cpd;
+  long long a_off_k[8];
+  short dWk[8], dHk[8], dTk[8];
   int dbg_skip;  // development: 1 = no epilogue data movement / stores, 2 = no TMA loads, 4 = one MMA per load
   long long a_off, a_sw, a_sh, a_st, a_sb;  // addend view: element offset / strides of (w,h,t,b) in the dst tensor
   signed char off_w[TC_MAX_LOADS], off_h[TC_MAX_LOADS], off_t[TC_MAX_LOADS];
@@ -118,8 +124,9 @@ template <int RS, int STATS, int MT>   // MT: 128-row sub-tiles per tile (compil
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmA2,
-                      const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ TcParams p,
-                      const __nv_bfloat16* __restrict__ addend, float* __restrict__ part, long long* __restrict__ dbg,
+                      const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD1,
+                      const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD3,
+                      const __grid_constant__ TcParams p, const __nv_bfloat16* __restrict__ addend, float* __restrict__ part, long long* __restrict__ dbg,
                       const __nv_bfloat16* __restrict__ yprev, const float* __restrict__ bn_ss) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -412,9 +419,16 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       named_bar_sync(BAR_SREADY + buf, BAR_HANDOFF);
       if (lane == 0) {
         const uint32_t staging_s = sbase + (uint32_t)(p.off_staging + buf * p.st_buf_bytes);
-        for (int ch = 0; ch < nst && !(p.dbg_skip & 1); ++ch)
-          tma_store_5d(&tmD, staging_s + (uint32_t)(ch * p.st_chunk_bytes), ti.n * p.Ntile + ch * p.cw, ti.w * p.bw,
-                       ti.h * p.bh, ti.t * p.bt, ti.b);
+        for (int ch = 0; ch < nst && !(p.dbg_skip & 1); ++ch) {
+          int col = ti.n * p.Ntile + ch * p.cw;
+          const CUtensorMap* dmap = &tmD;
+          if (STATS == 0 && p.ncls > 1) {   // stride-parity classes: chunk -> (class view, channel within the class)
+            const int k = col / p.cpd;
+            col -= k * p.cpd;
+            dmap = k == 0 ? &tmD : (k == 1 ? &tmD1 : (k == 2 ? &tmD2 : &tmD3));
+          }
+          tma_store_5d(dmap, staging_s + (uint32_t)(ch * p.st_chunk_bytes), col, ti.w * p.bw, ti.h * p.bh, ti.t * p.bt, ti.b);
+        }
         tma_store_commit();
         tma_store_wait_read();   // this tile's store has finished reading its staging buffer
         // publish "tiles 0..it have left their staging buffers": the epilogue warps poll this counter (a ~30-cycle
@@ -472,14 +486,24 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       // per 128-row sub-tile: pixel coordinates, validity, row offset in the destination tensor
       bool valid_m[MT];
       int64_t roff_m[MT];
+      const bool cls = STATS == 0 && p.ncls > 1;   // stride-parity classes (MT == 1): the addend origin depends on the column
+      int cw0 = 0, ch0 = 0, ct0 = 0;
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         const int w = ti.w * bw_ + lw[m], h = ti.h * bh_ + lh[m], t = ti.t * bt_ + lt[m];
         valid_m[m] = (w < dW_) && (h < dH_) && (t < dT_);
         roff_m[m] = 0;
         if (STATS != 1 && (p.has_addend || STATS == 2) && valid_m[m])
-          roff_m[m] = p.a_off + (int64_t)b * p.a_sb + (int64_t)t * p.a_st + (int64_t)h * p.a_sh + (int64_t)w * p.a_sw + n_idx * p.Ntile;
+          roff_m[m] = (cls ? 0 : p.a_off + n_idx * p.Ntile) + (int64_t)b * p.a_sb + (int64_t)t * p.a_st + (int64_t)h * p.a_sh + (int64_t)w * p.a_sw;
+        if (m == 0) { cw0 = w; ch0 = h; ct0 = t; }
       }
+      // addend row of 16 consecutive destination channels starting at tile column c (class mode: nullptr outside the class's extent)
+      auto cls_addend = [&](int c) -> const __nv_bfloat16* {
+        const int g = n_idx * p.Ntile + c;
+        const int k = g / p.cpd;
+        if (!(cw0 < p.dWk[k] && ch0 < p.dHk[k] && ct0 < p.dTk[k])) return nullptr;
+        return addend + p.a_off_k[k] + roff_m[0] + (g - k * p.cpd);
+      };
       const bool valid0 = valid_m[0];
       // STATS == 2: this pixel's row of the producing layer's conv output, fetched before the accumulator wait
       uint4 yq[STATS == 2 ? 2 * RS : 1];
@@ -547,8 +571,9 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = lrelu(fmaf(f[j], ep_sc[cg + j], ep_sh[cg + j]), p.slope);
         }
-        if (arow != nullptr) {
-          const f8 a0 = ld8(arow + c), a1 = ld8(arow + c + 8);
+        const __nv_bfloat16* ap = arow == nullptr ? nullptr : (cls ? cls_addend(c) : arow + c);
+        if (ap != nullptr) {
+          const f8 a0 = ld8(ap), a1 = ld8(ap + 8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { f[j] += a0.v[j]; f[8 + j] += a1.v[j]; }
           if (epi_bn) {
@@ -585,9 +610,10 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                   for (int k = 0; k < 16; ++k) f[k] = lrelu(fmaf(f[k], ep_sc[c + k], ep_sh[c + k]), p.slope);
                 }
-                if (STATS != 1 && arow != nullptr) {
-                  const int c = cbeg + 16 * (j0 + jj);
-                  const f8 a0 = ld8(arow + c), a1 = ld8(arow + c + 8);
+                const __nv_bfloat16* ap = (STATS == 1 || arow == nullptr) ? nullptr
+                                          : (cls ? cls_addend(cbeg + 16 * (j0 + jj)) : arow + cbeg + 16 * (j0 + jj));
+                if (STATS != 1 && ap != nullptr) {
+                  const f8 a0 = ld8(ap), a1 = ld8(ap + 8);
 #pragma unroll
                   for (int k = 0; k < 8; ++k) { f[k] += a0.v[k]; f[8 + k] += a1.v[k]; }
                   if (STATS == 0 && epi_bn) {
@@ -795,7 +821,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64, g_opt_mt = 0;
+static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64, g_opt_mt = 0, g_opt_classes = 1;
 int tc_option(const char* name, int value, bool set) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_opt_halo;
@@ -814,6 +840,7 @@ int tc_option(const char* name, int value, bool set) {
   else if (!strcmp(name, "tc_acc4")) slot = &g_opt_acc4;
   else if (!strcmp(name, "tc_bwd_stats_max")) slot = &g_opt_bwd_stats_max;
   else if (!strcmp(name, "tc_mt")) slot = &g_opt_mt;
+  else if (!strcmp(name, "tc_classes")) slot = &g_opt_classes;
   if (slot == nullptr) return -1;
   if (set) *slot = value;
   return *slot;
@@ -847,7 +874,7 @@ struct TcPlan {
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, bool bwd_stats, int MT) {
+static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, bool bwd_stats, int MT, int cls_cpd = 0) {
   const int PT = 128 * MT;   // pixels per tile
   if (!g_opt_tc) return false;
   const int taps = g.kt * g.kh * g.kw;
@@ -864,6 +891,7 @@ static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, 
   p.n_ntiles = (g.dC + 255) / 256;
   if (g.dC % (16 * p.n_ntiles)) return false;
   p.Ntile = g.dC / p.n_ntiles;
+  if (cls_cpd && (MT != 1 || has_stats || p.Ntile % cls_cpd)) return false;   // an N tile holds whole stride-parity classes
   // K blocking
   p.CB = g.sC <= 16 ? 16 : (g.sC <= 32 ? 32 : 64);
   p.ncblk = (g.sC + p.CB - 1) / p.CB;
@@ -899,8 +927,10 @@ static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, 
   p.drain_rs = (!has_stats || p.reg_stats) ? ((p.Ntile >> 4) + 1) / 2 : 0;
   p.mma_stats = (has_stats && !p.reg_stats && g_opt_mma_stats && p.n_ntiles == 1 && p.Ntile <= 128) ? 1 : 0;
   const bool chunked = p.n_ntiles == 1 && (p.mma_stats || ((!has_stats || p.reg_stats) && g_opt_chunked));
+  if (cls_cpd && !chunked && p.Ntile != cls_cpd) return false;   // one unswizzled chunk = the whole tile = one class
   if (chunked) {
     p.cw = p.Ntile > 32 ? 64 : (p.Ntile == 32 ? 32 : 16);
+    if (cls_cpd) p.cw = cls_cpd % 64 == 0 ? 64 : (cls_cpd % 32 == 0 ? 32 : 16);   // a staging chunk never straddles two classes
     p.st_mask = p.cw == 64 ? 7 : (p.cw == 32 ? 3 : 1);
     p.st_layout = p.cw == 64 ? 2 : (p.cw == 32 ? 4 : 6);
   } else {
@@ -1078,9 +1108,9 @@ static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, 
 
 // 256-pixel tiles (two 128-row MMA sub-tiles per handshake round) when they keep both MMA warps busy and leave enough
 // tiles per CTA; else the 128-pixel plan
-static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, bool bwd_stats = false) {
-  const bool ok1 = plan_gather_mt(g, has_stats, out, bwd_stats, 1);
-  if (g_opt_mt == 1) return ok1;
+static bool plan_gather(const GatherProblem& g, bool has_stats, TcPlan* out, bool bwd_stats = false, int cls_cpd = 0) {
+  const bool ok1 = plan_gather_mt(g, has_stats, out, bwd_stats, 1, cls_cpd);
+  if (g_opt_mt == 1 || cls_cpd) return ok1;
   TcPlan big;
   if (!plan_gather_mt(g, has_stats, &big, bwd_stats, 2)) return ok1;
   // measured rule (scripts/role_variants.py): the larger tile wins unless it costs the second MMA-issuing warp
@@ -1144,12 +1174,68 @@ static int encode_wgt_map(CUtensorMap* m, const void* ptr, int Ktot, int rows, i
   return DP_OK;
 }
 
+// All stride-parity classes of a strided data gradient as ONE stride-1 gather over dy: position (pt,ph,pw) of the combined
+// kernel reads dy at offset omin + p; its weight for class r is w[.., j] with j = r + pad - s * (omin + p) (zero block when j
+// falls outside the kernel); destination columns are [class][Cp] (dgrad_class() is the one-class-per-launch form).
+struct ClassGeom {
+  int ncls;
+  int r[8][3];      // (rt, rh, rw) of class k = (rt * sh + rh) * sw + rw
+  int vd[8][3];     // extent of the class's view of dx
+  int no[3], omin[3], maxd[3];
+};
+
+static bool class_geom(const dp_conv_desc* d, ClassGeom* cg) {
+  const int in[3] = {d->Ti, d->Hi, d->Wi}, k[3] = {d->kt, d->kh, d->kw}, st[3] = {d->st, d->sh, d->sw}, pad[3] = {d->pt, d->ph, d->pw};
+  cg->ncls = st[0] * st[1] * st[2];
+  if (cg->ncls < 2 || cg->ncls > 8) return false;
+  for (int i = 0; i < 3; ++i) {
+    if (in[i] < st[i]) return false;          // every class must own at least one pixel
+    int lo = 1 << 20, hi = -(1 << 20);
+    for (int r = 0; r < st[i]; ++r) {
+      const int j0 = (r + pad[i]) % st[i];
+      for (int j = j0; j < k[i]; j += st[i]) {
+        const int o = (r + pad[i] - j) / st[i];
+        lo = o < lo ? o : lo; hi = o > hi ? o : hi;
+      }
+    }
+    if (hi < lo) { lo = 0; hi = 0; }          // no class has a tap along this dim (cannot happen for k >= 1, s <= k + pad)
+    cg->omin[i] = lo; cg->no[i] = hi - lo + 1;
+    cg->maxd[i] = (in[i] + st[i] - 1) / st[i];
+  }
+  for (int rt = 0; rt < st[0]; ++rt)
+    for (int rh = 0; rh < st[1]; ++rh)
+      for (int rw = 0; rw < st[2]; ++rw) {
+        const int kk = (rt * st[1] + rh) * st[2] + rw;
+        const int r[3] = {rt, rh, rw};
+        for (int i = 0; i < 3; ++i) { cg->r[kk][i] = r[i]; cg->vd[kk][i] = (in[i] - r[i] + st[i] - 1) / st[i]; }
+      }
+  return true;
+}
+
+static GatherProblem class_problem(const dp_conv_desc* d, const ClassGeom& cg) {
+  GatherProblem g;
+  g.B = d->B;
+  g.sT = d->To; g.sH = d->Ho; g.sW = d->Wo; g.sC = d->Kp;
+  g.dT = cg.maxd[0]; g.dH = cg.maxd[1]; g.dW = cg.maxd[2]; g.dC = cg.ncls * d->Cp;
+  g.kt = cg.no[0]; g.kh = cg.no[1]; g.kw = cg.no[2];
+  g.Kt = cg.no[0]; g.Kh = cg.no[1]; g.Kw = cg.no[2];
+  g.mt = g.mh = g.mw = 1;
+  g.ot = cg.omin[0]; g.oh = cg.omin[1]; g.ow = cg.omin[2];
+  g.ts_t = g.ts_h = g.ts_w = 0;
+  g.tp_t = g.tp_h = g.tp_w = 1;
+  g.FT = d->Ti; g.FH = d->Hi; g.FW = d->Wi;
+  g.vo_t = g.vo_h = g.vo_w = 0;
+  g.vs_t = d->st; g.vs_h = d->sh; g.vs_w = d->sw;
+  g.ss_w = g.ss_h = g.ss_t = g.ss_b = 0;
+  return g;
+}
+
 static int launch_gather(const GatherProblem& g, const void* src, const void* wgt, void* dst, const void* addend,
                          float* part, int* nparts, cudaStream_t s, const void* yprev = nullptr, const float* bn_ss = nullptr,
-                         float slope = 1.f, int epi_bn = 0, float slope_res = 1.f) {
+                         float slope = 1.f, int epi_bn = 0, float slope_res = 1.f, const ClassGeom* cg = nullptr, int cpd = 0) {
   TcPlan plan;
   const bool bwd_stats = yprev != nullptr;
-  DP_REQUIRE(plan_gather(g, part != nullptr, &plan, bwd_stats), DP_ERR_UNSUPPORTED, "tcgen05 conv: geometry not supported");
+  DP_REQUIRE(plan_gather(g, part != nullptr, &plan, bwd_stats, cg ? cpd : 0), DP_ERR_UNSUPPORTED, "tcgen05 conv: geometry not supported");
   DP_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)wgt & 15) == 0 && ((uintptr_t)dst & 15) == 0, DP_ERR_ALIGN,
              "tcgen05 conv: tensors must be 16-byte aligned");
   TcParams& p = plan.p;
@@ -1184,14 +1270,36 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   p.a_st = (long long)g.vs_t * g.FH * g.FW * g.dC;
   p.a_sb = (long long)g.FT * g.FH * g.FW * g.dC;
   p.a_off = (((long long)g.vo_t * g.FH + g.vo_h) * g.FW + g.vo_w) * g.dC;
-  rc = encode_view_map(&tmD, (const __nv_bfloat16*)dst + p.a_off, g.dC, g.dW, g.dH, g.dT, g.B, p.a_sw, p.a_sh, p.a_st,
-                       p.a_sb, dbox, p.st_layout);
-  if (rc != DP_OK) return rc;
+  CUtensorMap tmDk[4];
+  if (cg == nullptr) {
+    rc = encode_view_map(&tmD, (const __nv_bfloat16*)dst + p.a_off, g.dC, g.dW, g.dH, g.dT, g.B, p.a_sw, p.a_sh, p.a_st,
+                         p.a_sb, dbox, p.st_layout);
+    if (rc != DP_OK) return rc;
+    tmDk[1] = tmDk[2] = tmDk[3] = tmD;
+  } else {
+    DP_REQUIRE(cg->ncls <= 4, DP_ERR_UNSUPPORTED, "tcgen05 dgrad classes: at most four classes per launch");
+    p.ncls = cg->ncls; p.cpd = cpd;
+    p.a_sw = (long long)g.vs_w * cpd;
+    p.a_sh = (long long)g.vs_h * g.FW * cpd;
+    p.a_st = (long long)g.vs_t * g.FH * g.FW * cpd;
+    p.a_sb = (long long)g.FT * g.FH * g.FW * cpd;
+    p.a_off = 0;
+    for (int k = 0; k < 4; ++k) {
+      const int kk = k < cg->ncls ? k : 0;
+      p.a_off_k[k] = (((long long)cg->r[kk][0] * g.FH + cg->r[kk][1]) * g.FW + cg->r[kk][2]) * cpd;
+      p.dTk[k] = (short)cg->vd[kk][0]; p.dHk[k] = (short)cg->vd[kk][1]; p.dWk[k] = (short)cg->vd[kk][2];
+      rc = encode_view_map(&tmDk[k], (const __nv_bfloat16*)dst + p.a_off_k[k], cpd, cg->vd[kk][2], cg->vd[kk][1], cg->vd[kk][0], g.B,
+                           p.a_sw, p.a_sh, p.a_st, p.a_sb, dbox, p.st_layout);
+      if (rc != DP_OK) return rc;
+    }
+    tmD = tmDk[0];
+  }
 
   static std::mutex attr_mu;
   static bool attr_done[DP_MAX_DEVICES] = {};   // cudaFuncSetAttribute is per device
   cudaError_t attr_err = cudaSuccess;
-  typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const __nv_bfloat16*, float*,
+  typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                         const CUtensorMap, const CUtensorMap, const TcParams, const __nv_bfloat16*, float*,
                          long long*, const __nv_bfloat16*, const float*);
   static KernFn const kerns[20] = {tc_gather_gemm_kernel<0, 0, 1>, tc_gather_gemm_kernel<1, 1, 1>, tc_gather_gemm_kernel<2, 1, 1>,
                                    tc_gather_gemm_kernel<3, 1, 1>, tc_gather_gemm_kernel<1, 0, 1>, tc_gather_gemm_kernel<2, 0, 1>,
@@ -1223,7 +1331,7 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
     DP_REQUIRE(!bwd_stats && p.drain_rs >= 1 && p.drain_rs <= (p.reg_stats ? 3 : 4), DP_ERR_UNSUPPORTED, "tcgen05 conv: no 256-pixel kernel for this shape");
     ki = p.reg_stats ? 12 + p.drain_rs : 15 + p.drain_rs;   // 13..15 / 16..19
   }
-  launch_pdl(kerns[ki], dim3(plan.grid), dim3(TC_THREADS), plan.smem, s, tmA, tmB, tmD, tmA2, tmB2, p, (const __nv_bfloat16*)addend, part, dbg,
+  launch_pdl(kerns[ki], dim3(plan.grid), dim3(TC_THREADS), plan.smem, s, tmA, tmB, tmD, tmA2, tmB2, tmDk[1], tmDk[2], tmDk[3], p, (const __nv_bfloat16*)addend, part, dbg,
              (const __nv_bfloat16*)yprev, bn_ss);
   if (getenv("DP_DEBUG_PLAN"))
     fprintf(stderr, "[tc_gather] dst %dx%dx%dx%d src C=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d CB=%d ncblk=%d Ntile=%d MT=%d stages=%d lps=%d dual=%d CBt=%d stats=%d/%d stage_bytes=%d a_box=%d tiles=%d grid=%d\n",
@@ -1355,6 +1463,58 @@ int tc_conv_fwd_view(const dp_conv_desc* d, const long long* xstrides, const voi
   GatherProblem g = fwd_problem(d);
   g.ss_w = xstrides[0]; g.ss_h = xstrides[1]; g.ss_t = xstrides[2]; g.ss_b = xstrides[3];
   return launch_gather(g, x, w, y, nullptr, part, nparts, s);
+}
+
+// ---- strided data gradient, all stride-parity classes in one launch ----
+size_t tc_dgrad_classes_weight_elems(const dp_conv_desc* d) {
+  if (d->dtype != DP_BF16 || (d->st == 1 && d->sh == 1 && d->sw == 1) || !g_opt_strided || !g_opt_classes) return 0;
+  ClassGeom cg;
+  if (!class_geom(d, &cg) || cg.ncls > 4) return 0;
+  TcPlan plan;
+  if (!plan_gather(class_problem(d, cg), false, &plan, false, d->Cp)) return 0;
+  return (size_t)cg.ncls * d->Cp * cg.no[0] * cg.no[1] * cg.no[2] * d->Kp;
+}
+
+// w_cls[(class k, c)][position (pt,ph,pw)][Kp] = w[kout][c][jt][jh][jw], j = r_k + pad - s * (omin + p); zero outside the kernel
+__global__ void pack_class_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, ClassGeom cg,
+                                          int K, int C, int Kp, int Cp, int kt, int kh, int kw, int st, int sh, int sw,
+                                          int pt, int ph, int pw) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int npos = cg.no[0] * cg.no[1] * cg.no[2];
+  const int64_t total = (int64_t)cg.ncls * Cp * npos * Kp;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ko = (int)(idx % Kp);
+  int64_t rest = idx / Kp;
+  const int pos = (int)(rest % npos); rest /= npos;
+  const int c = (int)(rest % Cp);
+  const int k = (int)(rest / Cp);
+  const int p2 = pos % cg.no[2], p1 = (pos / cg.no[2]) % cg.no[1], p0 = pos / (cg.no[2] * cg.no[1]);
+  const int jt = cg.r[k][0] + pt - st * (cg.omin[0] + p0);
+  const int jh = cg.r[k][1] + ph - sh * (cg.omin[1] + p1);
+  const int jw = cg.r[k][2] + pw - sw * (cg.omin[2] + p2);
+  float v = 0.f;
+  if (ko < K && c < C && jt >= 0 && jt < kt && jh >= 0 && jh < kh && jw >= 0 && jw < kw)
+    v = w[((((int64_t)ko * C + c) * kt + jt) * kh + jh) * kw + jw];
+  out[idx] = __float2bfloat16(v);
+}
+
+int tc_pack_dgrad_classes(const dp_conv_desc* d, const float* w, void* out, cudaStream_t s) {
+  ClassGeom cg;
+  DP_REQUIRE(tc_dgrad_classes_weight_elems(d) > 0 && class_geom(d, &cg), DP_ERR_UNSUPPORTED,
+             "dgrad classes: geometry not supported");
+  const int64_t total = (int64_t)tc_dgrad_classes_weight_elems(d);
+  launch_pdl(pack_class_weights_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, w, (__nv_bfloat16*)out, cg, d->K, d->C,
+             d->Kp, d->Cp, d->kt, d->kh, d->kw, d->st, d->sh, d->sw, d->pt, d->ph, d->pw);
+  return check_launch("pack_class_weights_kernel");
+}
+
+int tc_conv_dgrad_classes(const dp_conv_desc* d, const void* dy, const void* w_cls, const void* addend, void* dx, cudaStream_t s) {
+  ClassGeom cg;
+  DP_REQUIRE(tc_dgrad_classes_weight_elems(d) > 0 && class_geom(d, &cg), DP_ERR_UNSUPPORTED,
+             "dgrad classes: geometry not supported");
+  return launch_gather(class_problem(d, cg), dy, w_cls, dx, addend, nullptr, nullptr, s, nullptr, nullptr, 1.f, 0, 1.f, &cg, d->Cp);
 }
 
 int tc_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,

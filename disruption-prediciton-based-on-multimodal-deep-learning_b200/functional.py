@@ -142,7 +142,7 @@ def _p(t: Optional[torch.Tensor]):
 # ----------------------------------------------------------------------------------------------
 class ConvGeom:
     __slots__ = ("desc", "rows_out", "rows_in", "out_shape", "in_shape", "taps", "ws_bytes", "key", "flops", "esize",
-                 "fam", "stem")
+                 "fam", "stem", "cls")
 
     def __init__(self, C_in, K, kernel, stride, padding, B, T, H, W, dtype_code):
         kt, kh, kw = kernel
@@ -165,6 +165,18 @@ class ConvGeom:
         self.esize = 2 if dtype_code == L.DP_BF16 else 4
         self.fam = None
         self.stem = False   # True: x is the packed-rows clip of the stem fast path (csrc/stem.cu)
+        self.cls = None     # (impl, elements of the class-packed dgrad weights; 0 = per-class launches), see dgrad_classes()
+
+    def dgrad_classes(self, impl) -> int:
+        """Elements of the class-packed weights when the strided data gradient of this geometry runs as ONE launch
+        (dp_conv_dgrad_classes), else 0."""
+        if self.cls is None or self.cls[0] != impl:
+            n = 0
+            d = self.desc
+            if not self.stem and d.dtype == L.DP_BF16 and (d.st, d.sh, d.sw) != (1, 1, 1):
+                n = int(L.load().dp_dgrad_classes_weight_elems(C.byref(d), impl))
+            self.cls = (impl, n)
+        return self.cls[1]
 
     def families(self, impl):
         """Which kernel family serves fwd / dgrad / wgrad for this geometry (profiling labels)."""
@@ -352,9 +364,17 @@ def pack_weights(weight: torch.Tensor, geom: ConvGeom, dtype: torch.dtype, cache
                 "dp_stem_pack_weights")
     else:
         wf = torch.empty((d.Kp, geom.taps, d.Cp), dtype=dtype, device=weight.device)
-        wd = torch.empty((d.Cp, geom.taps, d.Kp), dtype=dtype, device=weight.device)
-        L.check(L.load().dp_pack_weights(C.byref(d), weight.data_ptr(), wf.data_ptr(), wd.data_ptr(), L.stream_ptr()),
-                "dp_pack_weights")
+        ncls = geom.dgrad_classes(_STATE["impl"]) if dtype == torch.bfloat16 else 0
+        if ncls:
+            # strided layer: the data gradient takes class-packed weights (all stride-parity classes in one launch)
+            wd = torch.empty(ncls, dtype=dtype, device=weight.device)
+            L.check(L.load().dp_pack_weights(C.byref(d), weight.data_ptr(), wf.data_ptr(), None, L.stream_ptr()), "dp_pack_weights")
+            L.check(L.load().dp_pack_weights_dgrad_classes(C.byref(d), weight.data_ptr(), wd.data_ptr(), L.stream_ptr()),
+                    "dp_pack_weights_dgrad_classes")
+        else:
+            wd = torch.empty((d.Cp, geom.taps, d.Kp), dtype=dtype, device=weight.device)
+            L.check(L.load().dp_pack_weights(C.byref(d), weight.data_ptr(), wf.data_ptr(), wd.data_ptr(), L.stream_ptr()),
+                    "dp_pack_weights")
     if cache is not None:
         cache.version, cache.ptr, cache.dtype, cache.wf, cache.wd = version, weight.data_ptr(), dtype, wf, wd
     return wf, wd
@@ -525,6 +545,9 @@ def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope
                                               y_prev.data_ptr(), stats_prev[2].data_ptr(), float(slope_prev),
                                               npart.data_ptr(), C.byref(nn_), impl, st), "dp_conv_dgrad_bnstats")
             box.append((npart, nn_))
+        elif wd.dim() == 1:     # class-packed weights (pack_weights): every stride-parity class in one launch
+            L.check(lib.dp_conv_dgrad_classes(C.byref(d), dy.data_ptr(), wd.data_ptr(), _p(addend), dx.data_ptr(), st),
+                    "dp_conv_dgrad_classes")
         else:
             L.check(lib.dp_conv_dgrad(C.byref(d), dy.data_ptr(), wd.data_ptr(), _p(addend), dx.data_ptr(), impl, st),
                     "dp_conv_dgrad")
@@ -630,8 +653,12 @@ class ConvFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            L.check(lib.dp_conv_dgrad(C.byref(d), dy.data_ptr(), wd.data_ptr(), None, dx.data_ptr(), impl, st),
-                    "dp_conv_dgrad")
+            if wd.dim() == 1:
+                L.check(lib.dp_conv_dgrad_classes(C.byref(d), dy.data_ptr(), wd.data_ptr(), None, dx.data_ptr(), st),
+                        "dp_conv_dgrad_classes")
+            else:
+                L.check(lib.dp_conv_dgrad(C.byref(d), dy.data_ptr(), wd.data_ptr(), None, dx.data_ptr(), impl, st),
+                        "dp_conv_dgrad")
         return dx, dw, None
 
 

@@ -118,6 +118,17 @@ int dp_conv_fwd_bnact(const dp_conv_desc* d, const long long* xstrides, const vo
 /* dx = conv_transpose(dy, w) (+ addend if non-NULL, same shape as dx). */
 int dp_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend,
                   void* dx, int impl, void* stream);
+/* Strided data gradient with EVERY stride-parity class in one launch (tcgen05 family, bf16).  The autograd of a strided
+ * nn.Conv3d (R2Plus1D.py:44-51 with stride (1,2,2) / (2,1,1): the down-sampling blocks :172-176) scatters dy into
+ * s_t*s_h*s_w interleaved pixel classes of dx; each class is a stride-1 gather over dy with a subset of the taps.
+ * dp_conv_dgrad runs one launch per class (each re-reading dy); here the classes are the column blocks of ONE stride-1
+ * gather whose weights w_cls[(class,c)][position][Kp] hold the class's tap (or zeros) for every dy offset, so dy is read
+ * once.  dp_dgrad_classes_weight_elems: elements of w_cls, 0 when the geometry is not covered (use dp_conv_dgrad);
+ * dp_pack_weights_dgrad_classes: fp32 master (K,C,kt,kh,kw) -> w_cls. */
+size_t dp_dgrad_classes_weight_elems(const dp_conv_desc* d, int impl);
+int dp_pack_weights_dgrad_classes(const dp_conv_desc* d, const float* w, void* w_cls, void* stream);
+int dp_conv_dgrad_classes(const dp_conv_desc* d, const void* dy, const void* w_cls, const void* addend, void* dx,
+                          void* stream);
 /* dp_conv_dgrad plus the two per-channel sums the BatchNorm backward of the layer that PRODUCED x needs (the
  * autograd of Conv3dBlock, R2Plus1D.py:44-54): with g = dx, yp = that layer's raw conv output (same shape as dx),
  * g' = g * lrelu'(scale*yp + shift):  part[nparts][2][Cp] = (sum g', sum g'*yp) -- the same partials

@@ -89,7 +89,9 @@ def run_conv(geom, B, dtype, impl, x, w, dy=None, addend=None):
     xi = to_int(x, dtype)
     gm = Fn.conv_geom(Cc, K, k, s, p, xi)
     d = gm.desc
-    wf, wd = Fn.pack_weights(w.contiguous(), gm, dtype, None)
+    wf = torch.empty((d.Kp, gm.taps, d.Cp), dtype=dtype, device=DEV)
+    wd = torch.empty((d.Cp, gm.taps, d.Kp), dtype=dtype, device=DEV)
+    L.check(lib.dp_pack_weights(C.byref(d), w.contiguous().data_ptr(), wf.data_ptr(), wd.data_ptr(), L.stream_ptr()), "pack")
     y = torch.empty(gm.out_shape, dtype=dtype, device=DEV)
     part = torch.zeros((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=DEV)
     nparts = C.c_int(0)
@@ -195,19 +197,37 @@ def _tc_check(geom, B, seed=0):
         assert res["fwd"] < 2 ** -7, res
         assert res["sum"] < 1e-3 and res["sq"] < 1e-3, res
     if lib.dp_conv_supported(C.byref(d), 1, L.IMPL_TC):
-        wf, wd = Fn.pack_weights(w.contiguous(), gm, torch.bfloat16, None)
+        # one launch per stride-parity class (dp_conv_dgrad, [Cp][taps][Kp] weights) and -- strided geometries -- every class
+        # in ONE launch over class-packed weights (dp_conv_dgrad_classes): both against the fp64 conv_transpose
+        wd = torch.empty((d.Cp, gm.taps, d.Kp), dtype=torch.bfloat16, device=DEV)
+        L.check(lib.dp_pack_weights(C.byref(d), w.contiguous().data_ptr(), None, wd.data_ptr(), L.stream_ptr()), "pack")
+        n_cls = int(lib.dp_dgrad_classes_weight_elems(C.byref(d), L.IMPL_TC))
+        if n_cls:
+            wc = torch.empty(n_cls, dtype=torch.bfloat16, device=DEV)
+            L.check(lib.dp_pack_weights_dgrad_classes(C.byref(d), w.contiguous().data_ptr(), wc.data_ptr(), L.stream_ptr()), "pack classes")
         dyi = to_int(dy, torch.bfloat16)
         for use_add in (False, True):
             ad = torch.randn_like(x).bfloat16().float() if use_add else None
             adi = to_int(ad, torch.bfloat16) if use_add else None
-            dx = torch.full(gm.in_shape, float("nan"), dtype=torch.bfloat16, device=DEV)
-            L.check(lib.dp_conv_dgrad(C.byref(d), dyi.data_ptr(), wd.data_ptr(),
-                                      None if adi is None else adi.data_ptr(), dx.data_ptr(), L.IMPL_TC,
-                                      L.stream_ptr()), "tc dgrad")
-            torch.cuda.synchronize()
             want = ref["dx"] + (ad.double() if use_add else 0)
-            res["dgrad_add" if use_add else "dgrad"] = rel_err(from_int(dx, Cc), want)
-            assert res["dgrad_add" if use_add else "dgrad"] < 2 ** -7, res
+            for path in (("per_class", "classes") if n_cls else ("per_class",)):
+                dx = torch.full(gm.in_shape, float("nan"), dtype=torch.bfloat16, device=DEV)
+                if path == "classes":
+                    L.check(lib.dp_conv_dgrad_classes(C.byref(d), dyi.data_ptr(), wc.data_ptr(),
+                                                      None if adi is None else adi.data_ptr(), dx.data_ptr(), L.stream_ptr()),
+                            "tc dgrad classes")
+                else:
+                    L.check(lib.dp_conv_dgrad(C.byref(d), dyi.data_ptr(), wd.data_ptr(),
+                                              None if adi is None else adi.data_ptr(), dx.data_ptr(), L.IMPL_TC,
+                                              L.stream_ptr()), "tc dgrad")
+                torch.cuda.synchronize()
+                key = ("dgrad_add" if use_add else "dgrad") + ("_cls" if path == "classes" else "")
+                assert torch.isfinite(dx.float()).all(), f"{key}: unwritten (NaN) elements of dx"
+                assert (dx[..., Cc:] == 0).all() or use_add, f"{key}: padded input channels must stay zero"
+                res[key] = rel_err(from_int(dx, Cc), want)
+                assert res[key] < 2 ** -7, res
+        if (d.st, d.sh, d.sw) != (1, 1, 1) and (T % d.st == 0 or True):
+            res["classes_in_one_launch"] = bool(n_cls)
     if lib.dp_conv_supported(C.byref(d), 2, L.IMPL_TC):
         dyi = to_int(dy, torch.bfloat16)
         dw = torch.empty_like(w)
@@ -226,6 +246,8 @@ def test_conv_tcgen05(geom):
     res = _tc_check(geom, B=2)
     print(geom, res)
     assert "fwd" in res and "wgrad" in res, "every geometry of the path has a tcgen05 forward and weight-gradient kernel"
+    if geom[3] != (1, 1, 1) and geom[0] <= 256:
+        assert res.get("classes_in_one_launch"), "strided data gradients of the R(2+1)D path run as one launch"
 
 
 def test_conv_tcgen05_modes():

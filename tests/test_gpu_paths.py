@@ -61,12 +61,27 @@ def test_sliding_window_matches_reference_loop():
             shards = [inference.sliding_window_probs(model, fr, seq_len, dist, batch_size=5,
                                                      window_range=dp_b200.distributed.shard_range(n_win, r, 3)).cpu()
                       for r in range(3)]
+            # the same windows without the CUDA-graph replay, without the per-frame stem cache, and after a weight change
+            pe = inference.sliding_window_probs(model, fr, seq_len, dist, batch_size=8, use_graph=False).cpu()
+            pn = inference.sliding_window_probs(model, fr, seq_len, dist, batch_size=8, stem_cache=False).cpu()
+        assert torch.allclose(pe, p8, atol=1e-6), mode                  # graph replay == eager launches, bit for bit up to softmax
+        assert (pn - ref).abs().max().item() < tol
         assert p8.shape == (n_win,)
         print(f"[{mode}] max |dP| vs reference loop: {(p8 - ref).abs().max().item():.3e}")
         assert (p8 - ref).abs().max().item() < tol
         assert (p1 - ref).abs().max().item() < tol
         assert torch.allclose(torch.cat(shards), p8, atol=1e-6 if mode == "fp32" else 2e-2)
     assert model.training is False
+    # captured graphs hold packed weight copies: a weight update must invalidate them
+    with dp_b200.compute_mode("bf16"):
+        before = inference.sliding_window_probs(model, fr, seq_len, dist, batch_size=8).cpu()
+        with torch.no_grad():
+            model.linear[3].bias.add_(torch.tensor([0.5, -0.5], device=DEV))
+            model.res2plus1d.conv5.block1.conv2.temporal_conv.conv.weight.mul_(1.5)
+        after_graph = inference.sliding_window_probs(model, fr, seq_len, dist, batch_size=8).cpu()
+        after_eager = inference.sliding_window_probs(model, fr, seq_len, dist, batch_size=8, use_graph=False).cpu()
+    assert (before - after_graph).abs().max().item() > 1e-3
+    assert torch.allclose(after_graph, after_eager, atol=1e-6)
     curve = inference.postprocess_curve(ref.tolist(), clip_len=seq_len, frame_srt=2)
     assert len(curve) == seq_len + 2 + n_win - 2
 
