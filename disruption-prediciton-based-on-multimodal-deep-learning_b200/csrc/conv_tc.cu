@@ -522,6 +522,27 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
       }
 
+      // addend (shortcut / residual gradient) rows of this pixel, fetched BEFORE the accumulator wait: issued inside the drain
+      // their L2 / HBM latency sat on the critical path of every chunk pair (measured: +170 us on the conv3 strided dgrad)
+      constexpr bool APF = STATS == 0 && MT == 1 && RS >= 1 && RS <= 4;
+      uint4 aq[APF ? 2 * RS : 1];
+      const bool apf = APF && p.has_addend != 0;
+      if (apf) {
+        const int nch = (cend - cbeg) >> 4;
+#pragma unroll
+        for (int j = 0; j < (APF ? RS : 0); ++j) {
+          const __nv_bfloat16* ap = nullptr;
+          if (j < nch && valid0) ap = cls ? cls_addend(cbeg + 16 * j) : addend + roff_m[0] + cbeg + 16 * j;
+          if (ap != nullptr) {
+            aq[2 * j] = *reinterpret_cast<const uint4*>(ap);
+            aq[2 * j + 1] = *reinterpret_cast<const uint4*>(ap + 8);
+          } else {
+            aq[2 * j] = make_uint4(0, 0, 0, 0);
+            aq[2 * j + 1] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+
       const long long c0 = edbg ? clock64() : 0;
       mbar_wait(tfull_bar(acc), acc_phase);
       if (edbg) w_tf += clock64() - c0;
@@ -610,7 +631,19 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                   for (int k = 0; k < 16; ++k) f[k] = lrelu(fmaf(f[k], ep_sc[c + k], ep_sh[c + k]), p.slope);
                 }
-                const __nv_bfloat16* ap = (STATS == 1 || arow == nullptr) ? nullptr
+                if (apf) {   // prefetched rows (zeros where this pixel / class has no addend)
+                  const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&aq[APF ? 2 * (j0 + jj) : 0]);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const float2 av = __bfloat1622float2(a2[k]);
+                    f[2 * k] += av.x; f[2 * k + 1] += av.y;
+                  }
+                  if (STATS == 0 && epi_bn) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) f[k] = lrelu(f[k], p.slope_res);
+                  }
+                }
+                const __nv_bfloat16* ap = (STATS == 1 || arow == nullptr || apf) ? nullptr
                                           : (cls ? cls_addend(cbeg + 16 * (j0 + jj)) : arow + cbeg + 16 * (j0 + jj));
                 if (STATS != 1 && ap != nullptr) {
                   const f8 a0 = ld8(ap), a1 = ld8(ap + 8);
@@ -948,9 +981,13 @@ static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, 
   p.acc_bufs = (p.mma_stats && 4 * p.Ntile > 512) ? 1 : ((!p.mma_stats && g_opt_acc4 && 4 * MT * p.Ntile <= 512) ? 4 : 2);
   if (MT == 2 && (p.n_ntiles != 1 || p.mma_stats || (has_stats && !p.reg_stats) || bwd_stats || 2 * MT * p.Ntile > 512)) return false;
   const int wgt_total = used_taps * p.w_row_bytes;
-  p.w_resident = (g_opt_resident && p.n_ntiles == 1 && wgt_total <= 98304) ? 1 : 0;
+  // class-packed weights of a strided data gradient (4 classes x 4 positions x 128 x 32 channels = 128 KB) stay resident too:
+  // streamed per stage they cost more shared-memory fill than the activations
+  p.w_resident = (g_opt_resident && p.n_ntiles == 1 && wgt_total <= (cls_cpd ? 131072 : 98304)) ? 1 : 0;
   const int stats_bytes = round_up(2 * g.dC * 4, 16);
-  const int misc = 2048 /*ones*/ + stats_bytes + 16384 /*scratch*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+  // the all-ones operand exists only for the statistics MMAs, the reduction scratch only with statistics
+  const int ones_bytes = p.mma_stats ? 2048 : 0, scratch_bytes = has_stats ? 16384 : 0;
+  const int misc = ones_bytes + stats_bytes + scratch_bytes + 256 /*barriers*/ + 1024 /*alignment*/;
   p.st_bufs = g_opt_st_bufs == 1 ? 1 : 2;
   auto fixed_bytes = [&]() { return p.st_bufs * p.st_buf_bytes + (p.w_resident ? wgt_total : 0) + misc; };
   const int fixed = fixed_bytes();   // tile search budget (refined below)
@@ -1088,9 +1125,9 @@ static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, 
   p.off_wgt = stages * p.stage_bytes;
   p.off_staging = p.off_wgt + (p.w_resident ? wgt_total : 0);
   p.off_ones = p.off_staging + p.st_bufs * p.st_buf_bytes;
-  p.off_stats = p.off_ones + 2048;
+  p.off_stats = p.off_ones + ones_bytes;
   p.off_scratch = p.off_stats + stats_bytes;
-  p.off_bars = p.off_scratch + 16384;
+  p.off_bars = p.off_scratch + scratch_bytes;
   int cols = 32;
   const int need_cols = (p.acc_bufs * MT + (p.mma_stats ? 2 : 0)) * p.Ntile;
   while (cols < need_cols) cols <<= 1;
@@ -1470,8 +1507,14 @@ size_t tc_dgrad_classes_weight_elems(const dp_conv_desc* d) {
   if (d->dtype != DP_BF16 || (d->st == 1 && d->sh == 1 && d->sw == 1) || !g_opt_strided || !g_opt_classes) return 0;
   ClassGeom cg;
   if (!class_geom(d, &cg) || cg.ncls > 4) return 0;
+  // 1x1x1 strided shortcuts have one class with a tap: a single launch plus a copy of the addend beats computing zeros
+  if (d->kt * d->kh * d->kw == 1) return 0;
   TcPlan plan;
   if (!plan_gather(class_problem(d, cg), false, &plan, false, d->Cp)) return 0;
+  // measured rule (scripts/strided_dgrad_bench.py, B = 64): a temporal stride-2 layer with many tiles per SM is bound by the
+  // epilogue of its 2 x Cp wide tile and gains nothing from reading dy once (conv3: 155 vs 120 us); the short ones gain from
+  // the saved launch (conv4 / conv5: 28 vs 34, 17 vs 26 us)
+  if (d->sh == 1 && d->sw == 1 && plan.p.num_tiles > 20 * num_sms()) return 0;
   return (size_t)cg.ncls * d->Cp * cg.no[0] * cg.no[1] * cg.no[2] * d->Kp;
 }
 

@@ -37,17 +37,17 @@ for (name, cin, cout, k, s, p, inp) in LAYERS:
     wd = torch.empty((d.Cp, gm.taps, d.Kp), dtype=torch.bfloat16, device=dev)
     L.check(lib.dp_pack_weights(C.byref(d), w.data_ptr(), None, wd.data_ptr(), L.stream_ptr()))
     dy = torch.randn(gm.out_shape, device=dev).bfloat16(); dy[..., cout:] = 0
-    ad = torch.randn_like(x)
+    ad = torch.randn_like(x) if (k == (1, 3, 3)) else None     # only a block's first conv receives the shortcut gradient
     dx = torch.empty_like(x)
     st = L.stream_ptr()
-    t_a = run(lambda: L.check(lib.dp_conv_dgrad(C.byref(d), dy.data_ptr(), wd.data_ptr(), ad.data_ptr(), dx.data_ptr(), L.IMPL_TC, st)))
+    t_a = run(lambda: L.check(lib.dp_conv_dgrad(C.byref(d), dy.data_ptr(), wd.data_ptr(), (ad.data_ptr() if ad is not None else None), dx.data_ptr(), L.IMPL_TC, st)))
     ref = dx.clone()
     n = int(lib.dp_dgrad_classes_weight_elems(C.byref(d), L.IMPL_TC))
     if n:
         wc = torch.empty(n, dtype=torch.bfloat16, device=dev)
         L.check(lib.dp_pack_weights_dgrad_classes(C.byref(d), w.data_ptr(), wc.data_ptr(), st))
         os.environ["DP_DEBUG_PLAN"] = "1"
-        t_b = run(lambda: L.check(lib.dp_conv_dgrad_classes(C.byref(d), dy.data_ptr(), wc.data_ptr(), ad.data_ptr(), dx.data_ptr(), st)))
+        t_b = run(lambda: L.check(lib.dp_conv_dgrad_classes(C.byref(d), dy.data_ptr(), wc.data_ptr(), (ad.data_ptr() if ad is not None else None), dx.data_ptr(), st)))
         same = bool(torch.equal(ref, dx)) or float((ref.float() - dx.float()).abs().max())
     else:
         t_b, same = float("nan"), "n/a"
