@@ -32,8 +32,20 @@ class ConvDesc(C.Structure):
         "kt", "kh", "kw", "st", "sh", "sw", "pt", "ph", "pw", "dtype")]
 
 
+class BnFin(C.Structure):
+    """Mirror of `dp_bn_fin` (include/dp_b200.h): BatchNorm finalisation run by the last CTA of the kernel that produces
+    the partial sums.  kind 1 = forward statistics, kind 2 = backward sums."""
+
+    _fields_ = [("kind", C.c_int32), ("C", C.c_int32), ("Cp", C.c_int32), ("coef_zero", C.c_int32), ("count", C.c_double),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("momentum", C.c_float),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+                ("mean", C.c_void_p), ("rstd", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("coef", C.c_void_p), ("ticket", C.c_void_p)]
+
+
 _vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 _pdesc = C.POINTER(ConvDesc)
+_pfin = C.POINTER(BnFin)
 _pint = C.POINTER(C.c_int)
 
 # name -> (restype, argtypes); exactly the declarations of include/dp_b200.h
@@ -60,6 +72,8 @@ SIGNATURES = {
     "dp_pack_weights_dgrad_classes": (_i, [_pdesc, _vp, _vp, _vp]),
     "dp_conv_dgrad_classes": (_i, [_pdesc, _vp, _vp, _vp, _vp, _vp]),
     "dp_conv_dgrad_bnstats": (_i, [_pdesc, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _pint, _i, _vp]),
+    "dp_conv_fwd_fin": (_i, [_pdesc, _vp, _vp, _vp, _vp, _pfin, _i, _vp]),
+    "dp_conv_dgrad_bnstats_fin": (_i, [_pdesc, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _pfin, _i, _vp]),
     "dp_conv_wgrad_workspace": (_sz, [_pdesc, _i]),
     "dp_conv_wgrad": (_i, [_pdesc, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "dp_stem_supported": (_i, [_pdesc]),
@@ -68,6 +82,7 @@ SIGNATURES = {
     "dp_stem_pack_input_u8": (_i, [_pdesc, _vp, C.POINTER(C.c_float), _vp, _vp]),
     "dp_stem_pack_weights": (_i, [_pdesc, _vp, _vp, _vp]),
     "dp_stem_conv_fwd": (_i, [_pdesc, _vp, _vp, _vp, _vp, _pint, _vp]),
+    "dp_stem_conv_fwd_fin": (_i, [_pdesc, _vp, _vp, _vp, _vp, _pfin, _vp]),
     "dp_stem_conv_fwd_bnact": (_i, [_pdesc, _vp, _vp, _vp, _f, _vp, _vp]),
     "dp_stem_wgrad_workspace": (_sz, [_pdesc]),
     "dp_stem_conv_wgrad": (_i, [_pdesc, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -76,6 +91,7 @@ SIGNATURES = {
     "dp_bn_eval_coeffs": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp]),
     "dp_bn_act_apply": (_i, [_vp, _vp, _vp, _f, _vp, _f, _vp, _i64, _i, _i, _vp]),
     "dp_bn_act_bwd_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _pint, _i64, _i, _i, _vp]),
+    "dp_bn_act_bwd_reduce_fin": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _i64, _i, _i, _pfin, _vp]),
     "dp_bn_bwd_finalize": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dp_bn_act_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _i64, _i, _i, _vp]),
     "dp_add": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
@@ -131,6 +147,11 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError here == header/library mismatch
             fn.restype = res
             fn.argtypes = args
+        # DP_OPTIONS="pdl=0,tc_mt=1": planner / launch options (dp_set_option) for A/B measurements
+        for item in filter(None, os.environ.get("DP_OPTIONS", "").split(",")):
+            name, _, value = item.partition("=")
+            if lib.dp_set_option(name.strip().encode(), int(value)) != DP_OK:
+                raise DpError(f"DP_OPTIONS: unknown option '{name}'")
         _lib = lib
     return _lib
 

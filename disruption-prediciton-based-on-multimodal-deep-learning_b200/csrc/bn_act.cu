@@ -7,6 +7,7 @@
 // residual add + LeakyReLU at :179-187 (and their autograd).
 #include "dp_common.cuh"
 #include "conv_internal.cuh"
+#include "bn_fin.cuh"
 
 namespace dp {
 
@@ -16,7 +17,7 @@ constexpr int RED_THREADS = 256;
 // F: __device__ void operator()(int64_t elem_offset, int c0, float* a8, float* b8) accumulates 8 channels
 template <typename F>
 __global__ void __launch_bounds__(RED_THREADS, 2)
-col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part) {  // f by value: per-thread register copy
+col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part, const dp_bn_fin fin) {  // f by value: per-thread register copy
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[2][RED_THREADS * 8];
@@ -56,6 +57,11 @@ col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part) {  // f 
     for (int rl = 0; rl < rpi; ++rl) { sa += red[0][rl * Cp + c]; sb += red[1][rl * Cp + c]; }
     part[((int64_t)blockIdx.x * 2 + 0) * Cp + c] = sa;
     part[((int64_t)blockIdx.x * 2 + 1) * Cp + c] = sb;
+  }
+  if (fin.kind) {   // last CTA done: finalise in this launch (bn_fin.cuh); `red` is free again after the barrier
+    __threadfence();
+    __syncthreads();
+    bn_fin_tail(fin, part, reinterpret_cast<int*>(&red[1][0]), reinterpret_cast<double*>(&red[0][0]));
   }
 }
 
@@ -105,86 +111,35 @@ struct BwdReduceF {
   }
 };
 
-int bn_stats_launch(const void* y, int64_t rows, int Cp, int dtype, float* part, int* nparts, cudaStream_t s) {
+static const dp_bn_fin kNoFin = {};   // kind 0: the kernel writes its partials and stops
+
+int bn_stats_launch(const void* y, int64_t rows, int Cp, int dtype, float* part, int* nparts, cudaStream_t s,
+                    const dp_bn_fin* fin) {
   DP_REQUIRE(Cp % 8 == 0 && Cp > 0 && Cp <= 1024, DP_ERR_ALIGN, "bn_stats: Cp=%d must be a multiple of 8, <= 1024", Cp);
   DP_REQUIRE(rows > 0, DP_ERR_SHAPE, "bn_stats: no rows");
   const int grid = reduce_grid(rows);
+  const dp_bn_fin f_ = fin ? *fin : kNoFin;
   if (dtype == DP_BF16) {
     StatsF<__nv_bfloat16> f{(const __nv_bfloat16*)y};
-    launch_pdl(col_reduce2_kernel<StatsF<__nv_bfloat16>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part);
+    launch_pdl(col_reduce2_kernel<StatsF<__nv_bfloat16>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
   } else {
     StatsF<float> f{(const float*)y};
-    launch_pdl(col_reduce2_kernel<StatsF<float>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part);
+    launch_pdl(col_reduce2_kernel<StatsF<float>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
   }
-  *nparts = grid;
+  if (nparts != nullptr) *nparts = grid;
   return check_launch("bn_stats");
 }
 
 // ---- finalize: partials -> mean/rstd/scale/shift, running stats (momentum, unbiased var) ----
-// One CTA of 256 threads per 32 channels: 8 part-lanes x 32 channel-lanes, fp64 partial sums combined in a fixed
-// order (deterministic), reads coalesced along the channel dimension.
-constexpr int FIN_CH = 32, FIN_PL = 8;
-__device__ __forceinline__ void fin_reduce(const float* __restrict__ part, int nparts, int Cp, int c, int pl, bool cval,
-                                           double& S, double& Q, double (*red)[FIN_PL][FIN_CH]) {
-  double s = 0.0, q = 0.0;
-  if (cval) {
-    // four independent load/accumulate chains per thread: the loop is pure memory latency (<= 592 partials), and this
-    // kernel sits on the critical path between every conv and its apply pass; the order stays fixed (deterministic)
-    double s1 = 0.0, q1 = 0.0, s2 = 0.0, q2 = 0.0, s3 = 0.0, q3 = 0.0;
-    int p = pl;
-    for (; p + 3 * FIN_PL < nparts; p += 4 * FIN_PL) {
-      const float a0 = part[((int64_t)p * 2 + 0) * Cp + c], b0 = part[((int64_t)p * 2 + 1) * Cp + c];
-      const float a1 = part[((int64_t)(p + FIN_PL) * 2 + 0) * Cp + c], b1 = part[((int64_t)(p + FIN_PL) * 2 + 1) * Cp + c];
-      const float a2 = part[((int64_t)(p + 2 * FIN_PL) * 2 + 0) * Cp + c], b2 = part[((int64_t)(p + 2 * FIN_PL) * 2 + 1) * Cp + c];
-      const float a3 = part[((int64_t)(p + 3 * FIN_PL) * 2 + 0) * Cp + c], b3 = part[((int64_t)(p + 3 * FIN_PL) * 2 + 1) * Cp + c];
-      s += (double)a0; q += (double)b0; s1 += (double)a1; q1 += (double)b1;
-      s2 += (double)a2; q2 += (double)b2; s3 += (double)a3; q3 += (double)b3;
-    }
-    for (; p < nparts; p += FIN_PL) {
-      s += (double)part[((int64_t)p * 2 + 0) * Cp + c];
-      q += (double)part[((int64_t)p * 2 + 1) * Cp + c];
-    }
-    s = (s + s1) + (s2 + s3);
-    q = (q + q1) + (q2 + q3);
-  }
-  const int cl = threadIdx.x % FIN_CH;
-  red[0][pl][cl] = s;
-  red[1][pl][cl] = q;
-  __syncthreads();
-  S = 0.0; Q = 0.0;
-  if (pl == 0) {
-#pragma unroll
-    for (int i = 0; i < FIN_PL; ++i) { S += red[0][i][cl]; Q += red[1][i][cl]; }
-  }
-}
-
+// One CTA of 256 threads per 32 channels (bn_fin.cuh: 8 part-lanes x 32 channel-lanes, fp64 partial sums combined in a
+// fixed order, reads coalesced along the channel dimension).  The producing kernels run the same code in their last
+// CTA when they are given a dp_bn_fin; these stand-alone launches serve partials that come without one.
 __global__ void __launch_bounds__(FIN_CH * FIN_PL)
-bn_finalize_kernel(const float* __restrict__ part, int nparts, int C, int Cp, double count,
-                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                   float momentum, float* running_mean, float* running_var,
-                   float* mean, float* rstd, float* scale, float* shift) {
-  __shared__ double red[2][FIN_PL][FIN_CH];
+bn_finalize_group_kernel(const float* __restrict__ part, int nparts, const dp_bn_fin fin) {
+  __shared__ double red[2 * FIN_PL * FIN_CH];
   pdl_launch_dependents();
   pdl_wait();
-  const int c = blockIdx.x * FIN_CH + threadIdx.x % FIN_CH, pl = threadIdx.x / FIN_CH;
-  double S, Q;
-  fin_reduce(part, nparts, Cp, c, pl, c < C, S, Q, red);
-  if (pl != 0 || c >= Cp) return;
-  if (c >= C) { mean[c] = 0.f; rstd[c] = 0.f; scale[c] = 0.f; shift[c] = 0.f; return; }
-  const double mu = S / count;
-  double var = Q / count - mu * mu;
-  if (var < 0.0) var = 0.0;
-  const float rs = (float)(1.0 / sqrt(var + (double)eps));
-  const float sc = gamma[c] * rs;
-  mean[c] = (float)mu;
-  rstd[c] = rs;
-  scale[c] = sc;
-  shift[c] = beta[c] - (float)mu * sc;
-  if (running_mean != nullptr) {
-    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-  }
+  bn_fin_group(fin, part, nparts, blockIdx.x * FIN_CH, threadIdx.x, red);
 }
 
 __global__ void bn_eval_coeffs_kernel(const float* rm, const float* rv, const float* gamma, const float* beta,
@@ -196,25 +151,6 @@ __global__ void bn_eval_coeffs_kernel(const float* rm, const float* rv, const fl
   const float sc = gamma[c] * rs;
   scale[c] = sc;
   shift[c] = beta[c] - rm[c] * sc;
-}
-
-__global__ void __launch_bounds__(FIN_CH * FIN_PL)
-bn_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, int Cp, double count,
-                       const float* __restrict__ mean, const float* __restrict__ rstd,
-                       float* dgamma, float* dbeta, float* coef) {
-  __shared__ double red[2][FIN_PL][FIN_CH];
-  pdl_launch_dependents();
-  pdl_wait();
-  const int c = blockIdx.x * FIN_CH + threadIdx.x % FIN_CH, pl = threadIdx.x / FIN_CH;
-  double S, Q;
-  fin_reduce(part, nparts, Cp, c, pl, c < C, S, Q, red);
-  if (pl != 0 || c >= Cp) return;
-  if (c >= C) { coef[c] = 0.f; coef[Cp + c] = 0.f; return; }
-  Q = (Q - (double)mean[c] * S) * (double)rstd[c];   // sum(g*y) -> sum(g*xhat)
-  if (dbeta != nullptr) dbeta[c] = (float)S;
-  if (dgamma != nullptr) dgamma[c] = (float)Q;
-  coef[c] = (float)(S / count);
-  coef[Cp + c] = (float)(Q / count);
 }
 
 // ---- elementwise passes ----
@@ -334,7 +270,7 @@ using namespace dp;
 
 DP_API int dp_bn_stats(const void* y, int64_t rows, int Cp, int dtype, float* part, int* nparts, void* stream) {
   DP_REQUIRE(y && part && nparts, DP_ERR_SHAPE, "dp_bn_stats: NULL pointer");
-  return bn_stats_launch(y, rows, Cp, dtype, part, nparts, as_stream(stream));
+  return bn_stats_launch(y, rows, Cp, dtype, part, nparts, as_stream(stream), nullptr);
 }
 
 DP_API int dp_bn_finalize(const float* part, int nparts, int C, int Cp, double count, const float* gamma,
@@ -345,8 +281,10 @@ DP_API int dp_bn_finalize(const float* part, int nparts, int C, int Cp, double c
              "dp_bn_finalize: bad sizes (nparts=%d C=%d Cp=%d)", nparts, C, Cp);
   DP_REQUIRE((running_mean == nullptr) == (running_var == nullptr), DP_ERR_SHAPE,
              "dp_bn_finalize: running_mean/var must both be given or both NULL");
-  launch_pdl(bn_finalize_kernel, dim3(ceil_div(Cp, FIN_CH)), dim3(FIN_CH * FIN_PL), 0, as_stream(stream), part, nparts, C, Cp, count,
-             gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift);
+  dp_bn_fin f = {};
+  f.kind = 1; f.C = C; f.Cp = Cp; f.count = count; f.gamma = gamma; f.beta = beta; f.eps = eps; f.momentum = momentum;
+  f.running_mean = running_mean; f.running_var = running_var; f.mean = mean; f.rstd = rstd; f.scale = scale; f.shift = shift;
+  launch_pdl(bn_finalize_group_kernel, dim3(ceil_div(Cp, FIN_CH)), dim3(FIN_CH * FIN_PL), 0, as_stream(stream), part, nparts, f);
   return check_launch("dp_bn_finalize");
 }
 
@@ -377,26 +315,43 @@ DP_API int dp_bn_act_apply(const void* y, const float* scale, const float* shift
   return check_launch("dp_bn_act_apply");
 }
 
+static int bwd_reduce_launch(const void* dz, const void* y, const void* out, const float* scale, const float* shift,
+                             const float* mean, const float* rstd, float slope, float slope_res, float* part, int* nparts,
+                             int64_t rows, int Cp, int dtype, void* stream, const dp_bn_fin* fin, const char* who) {
+  DP_REQUIRE(dz && y && scale && shift && mean && rstd && part, DP_ERR_SHAPE, "%s: NULL pointer", who);
+  DP_REQUIRE(Cp % 8 == 0 && Cp > 0 && Cp <= 1024 && rows > 0, DP_ERR_ALIGN, "%s: bad Cp=%d", who, Cp);
+  const int grid = reduce_grid(rows);
+  cudaStream_t s = as_stream(stream);
+  const dp_bn_fin f_ = fin ? *fin : kNoFin;
+  if (dtype == DP_BF16) {
+    BwdReduceF<__nv_bfloat16> f{(const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, (const __nv_bfloat16*)out,
+                                scale, shift, mean, rstd, slope, slope_res};
+    launch_pdl(col_reduce2_kernel<BwdReduceF<__nv_bfloat16>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+  } else {
+    BwdReduceF<float> f{(const float*)dz, (const float*)y, (const float*)out, scale, shift, mean, rstd, slope,
+                        slope_res};
+    launch_pdl(col_reduce2_kernel<BwdReduceF<float>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+  }
+  if (nparts != nullptr) *nparts = grid;
+  return check_launch(who);
+}
+
 DP_API int dp_bn_act_bwd_reduce(const void* dz, const void* y, const void* out, const float* scale,
                                 const float* shift, const float* mean, const float* rstd, float slope,
                                 float slope_res, float* part, int* nparts, int64_t rows, int Cp, int dtype,
                                 void* stream) {
-  DP_REQUIRE(dz && y && scale && shift && mean && rstd && part && nparts, DP_ERR_SHAPE,
-             "dp_bn_act_bwd_reduce: NULL pointer");
-  DP_REQUIRE(Cp % 8 == 0 && Cp > 0 && Cp <= 1024 && rows > 0, DP_ERR_ALIGN, "dp_bn_act_bwd_reduce: bad Cp=%d", Cp);
-  const int grid = reduce_grid(rows);
-  cudaStream_t s = as_stream(stream);
-  if (dtype == DP_BF16) {
-    BwdReduceF<__nv_bfloat16> f{(const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, (const __nv_bfloat16*)out,
-                                scale, shift, mean, rstd, slope, slope_res};
-    launch_pdl(col_reduce2_kernel<BwdReduceF<__nv_bfloat16>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part);
-  } else {
-    BwdReduceF<float> f{(const float*)dz, (const float*)y, (const float*)out, scale, shift, mean, rstd, slope,
-                        slope_res};
-    launch_pdl(col_reduce2_kernel<BwdReduceF<float>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part);
-  }
-  *nparts = grid;
-  return check_launch("dp_bn_act_bwd_reduce");
+  DP_REQUIRE(nparts != nullptr, DP_ERR_SHAPE, "dp_bn_act_bwd_reduce: NULL pointer");
+  return bwd_reduce_launch(dz, y, out, scale, shift, mean, rstd, slope, slope_res, part, nparts, rows, Cp, dtype, stream,
+                           nullptr, "dp_bn_act_bwd_reduce");
+}
+
+DP_API int dp_bn_act_bwd_reduce_fin(const void* dz, const void* y, const void* out, const float* scale,
+                                    const float* shift, float slope, float slope_res, float* part, int64_t rows, int Cp,
+                                    int dtype, const dp_bn_fin* fin, void* stream) {
+  const int rc = bn_fin_validate(fin, 2, Cp, "dp_bn_act_bwd_reduce_fin");
+  if (rc != DP_OK) return rc;
+  return bwd_reduce_launch(dz, y, out, scale, shift, fin->mean, fin->rstd, slope, slope_res, part, nullptr, rows, Cp, dtype,
+                           stream, fin, "dp_bn_act_bwd_reduce_fin");
 }
 
 DP_API int dp_bn_bwd_finalize(const float* part, int nparts, int C, int Cp, double count, const float* mean,
@@ -404,8 +359,10 @@ DP_API int dp_bn_bwd_finalize(const float* part, int nparts, int C, int Cp, doub
   DP_REQUIRE(part && coef && mean && rstd, DP_ERR_SHAPE, "dp_bn_bwd_finalize: NULL pointer");
   DP_REQUIRE(nparts > 0 && nparts <= DP_MAX_PARTS && C > 0 && Cp >= C && count > 0, DP_ERR_SHAPE,
              "dp_bn_bwd_finalize: bad sizes");
-  launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(Cp, FIN_CH)), dim3(FIN_CH * FIN_PL), 0, as_stream(stream), part, nparts, C, Cp,
-             count, mean, rstd, dgamma, dbeta, coef);
+  dp_bn_fin f = {};
+  f.kind = 2; f.C = C; f.Cp = Cp; f.count = count; f.mean = const_cast<float*>(mean); f.rstd = const_cast<float*>(rstd);
+  f.dgamma = dgamma; f.dbeta = dbeta; f.coef = coef;
+  launch_pdl(bn_finalize_group_kernel, dim3(ceil_div(Cp, FIN_CH)), dim3(FIN_CH * FIN_PL), 0, as_stream(stream), part, nparts, f);
   return check_launch("dp_bn_bwd_finalize");
 }
 

@@ -2,6 +2,7 @@
 // the tcgen05 kernels and the CUDA-core kernels.  No cuDNN, no CPU path.
 #include "dp_common.cuh"
 #include "conv_internal.cuh"
+#include "bn_fin.cuh"
 
 namespace dp {
 
@@ -100,23 +101,37 @@ DP_API int dp_conv_supported(const dp_conv_desc* d, int op, int impl) {
   return resolve_impl_query(d, op, impl) > 0 ? 1 : 0;
 }
 
-DP_API int dp_conv_fwd(const dp_conv_desc* d, const void* x, const void* w_fwd, void* y, float* part, int* nparts,
-                       int impl, void* stream) {
+static int conv_fwd_any(const dp_conv_desc* d, const void* x, const void* w_fwd, void* y, float* part, int* nparts,
+                        const dp_bn_fin* fin, int impl, void* stream, const char* who) {
   int rc = validate(d);
   if (rc != DP_OK) return rc;
-  DP_REQUIRE(x && w_fwd && y, DP_ERR_SHAPE, "dp_conv_fwd: NULL pointer");
-  DP_REQUIRE(part == nullptr || nparts != nullptr, DP_ERR_SHAPE, "dp_conv_fwd: part given without nparts");
+  DP_REQUIRE(x && w_fwd && y, DP_ERR_SHAPE, "%s: NULL pointer", who);
   const int r = resolve_impl(d, 0, impl);
-  DP_REQUIRE(r > 0, DP_ERR_UNSUPPORTED, "dp_conv_fwd: geometry not covered by the tcgen05 family");
+  DP_REQUIRE(r > 0, DP_ERR_UNSUPPORTED, "%s: geometry not covered by the tcgen05 family", who);
   cudaStream_t s = as_stream(stream);
-  if (r == DP_IMPL_TC) return tc_conv_fwd(d, x, w_fwd, y, part, nparts, s);
+  if (r == DP_IMPL_TC) return tc_conv_fwd(d, x, w_fwd, y, part, nparts, s, fin);
   rc = simt_conv_fwd(d, x, w_fwd, y, s);
   if (rc != DP_OK) return rc;
   if (part != nullptr) {
     const int64_t rows = (int64_t)d->B * d->To * d->Ho * d->Wo;
-    return bn_stats_launch(y, rows, d->Kp, d->dtype, part, nparts, s);
+    return bn_stats_launch(y, rows, d->Kp, d->dtype, part, nparts, s, fin);   // fin: last CTA of the reduction finalises
   }
   return DP_OK;
+}
+
+DP_API int dp_conv_fwd(const dp_conv_desc* d, const void* x, const void* w_fwd, void* y, float* part, int* nparts,
+                       int impl, void* stream) {
+  DP_REQUIRE(part == nullptr || nparts != nullptr, DP_ERR_SHAPE, "dp_conv_fwd: part given without nparts");
+  return conv_fwd_any(d, x, w_fwd, y, part, nparts, nullptr, impl, stream, "dp_conv_fwd");
+}
+
+DP_API int dp_conv_fwd_fin(const dp_conv_desc* d, const void* x, const void* w_fwd, void* y, float* part,
+                           const dp_bn_fin* fin, int impl, void* stream) {
+  DP_REQUIRE(d != nullptr && part != nullptr, DP_ERR_SHAPE, "dp_conv_fwd_fin: NULL pointer");
+  const int rc = bn_fin_validate(fin, 1, d->Kp, "dp_conv_fwd_fin");
+  if (rc != DP_OK) return rc;
+  int nparts = 0;
+  return conv_fwd_any(d, x, w_fwd, y, part, &nparts, fin, impl, stream, "dp_conv_fwd_fin");
 }
 
 DP_API unsigned long long dp_simt_launch_count(void) { return g_simt_launches; }
@@ -175,23 +190,45 @@ DP_API int dp_conv_dgrad_classes(const dp_conv_desc* d, const void* dy, const vo
   return tc_conv_dgrad_classes(d, dy, w_cls, addend, dx, as_stream(stream));
 }
 
-DP_API int dp_conv_dgrad_bnstats(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx,
-                                 const void* y_prev, const float* scale_shift, float slope, float* part, int* nparts,
-                                 int impl, void* stream) {
+static int conv_dgrad_bnstats_any(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx,
+                                  const void* y_prev, const float* scale_shift, float slope, float* part, int* nparts,
+                                  const dp_bn_fin* fin, int impl, void* stream, const char* who) {
   int rc = validate(d);
   if (rc != DP_OK) return rc;
-  DP_REQUIRE(dy && w_dgrad && dx && y_prev && scale_shift && part && nparts, DP_ERR_SHAPE, "dp_conv_dgrad_bnstats: NULL pointer");
+  DP_REQUIRE(dy && w_dgrad && dx && y_prev && scale_shift && part, DP_ERR_SHAPE, "%s: NULL pointer", who);
   const int r = resolve_impl(d, 1, impl);
-  DP_REQUIRE(r > 0, DP_ERR_UNSUPPORTED, "dp_conv_dgrad_bnstats: geometry not covered by the tcgen05 family");
+  DP_REQUIRE(r > 0, DP_ERR_UNSUPPORTED, "%s: geometry not covered by the tcgen05 family", who);
   cudaStream_t s = as_stream(stream);
   if (r == DP_IMPL_TC && tc_dgrad_bnstats_supported(d))
-    return tc_conv_dgrad_bnstats(d, dy, w_dgrad, addend, dx, y_prev, scale_shift, slope, part, nparts, s);
+    return tc_conv_dgrad_bnstats(d, dy, w_dgrad, addend, dx, y_prev, scale_shift, slope, part, nparts, s, fin);
   rc = (r == DP_IMPL_TC) ? tc_conv_dgrad(d, dy, w_dgrad, addend, dx, s) : simt_conv_dgrad(d, dy, w_dgrad, addend, dx, s);
   if (rc != DP_OK) return rc;
   const int64_t rows = (int64_t)d->B * d->Ti * d->Hi * d->Wi;
-  // mean / rstd are not read by the reduction (the raw-y sums are centred in dp_bn_bwd_finalize)
+  // mean / rstd are not read by the reduction (the raw-y sums are centred in the finalisation)
+  if (fin != nullptr)
+    return dp_bn_act_bwd_reduce_fin(dx, y_prev, nullptr, scale_shift, scale_shift + d->Cp, slope, 1.f, part, rows, d->Cp,
+                                    d->dtype, fin, stream);
   return dp_bn_act_bwd_reduce(dx, y_prev, nullptr, scale_shift, scale_shift + d->Cp, scale_shift, scale_shift, slope, 1.f, part,
                               nparts, rows, d->Cp, d->dtype, stream);
+}
+
+DP_API int dp_conv_dgrad_bnstats(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx,
+                                 const void* y_prev, const float* scale_shift, float slope, float* part, int* nparts,
+                                 int impl, void* stream) {
+  DP_REQUIRE(nparts != nullptr, DP_ERR_SHAPE, "dp_conv_dgrad_bnstats: NULL pointer");
+  return conv_dgrad_bnstats_any(d, dy, w_dgrad, addend, dx, y_prev, scale_shift, slope, part, nparts, nullptr, impl, stream,
+                                "dp_conv_dgrad_bnstats");
+}
+
+DP_API int dp_conv_dgrad_bnstats_fin(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend, void* dx,
+                                     const void* y_prev, const float* scale_shift, float slope, float* part,
+                                     const dp_bn_fin* fin, int impl, void* stream) {
+  DP_REQUIRE(d != nullptr, DP_ERR_SHAPE, "dp_conv_dgrad_bnstats_fin: NULL pointer");
+  const int rc = bn_fin_validate(fin, 2, d->Cp, "dp_conv_dgrad_bnstats_fin");
+  if (rc != DP_OK) return rc;
+  int nparts = 0;
+  return conv_dgrad_bnstats_any(d, dy, w_dgrad, addend, dx, y_prev, scale_shift, slope, part, &nparts, fin, impl, stream,
+                                "dp_conv_dgrad_bnstats_fin");
 }
 
 DP_API size_t dp_conv_wgrad_workspace(const dp_conv_desc* d, int impl) {

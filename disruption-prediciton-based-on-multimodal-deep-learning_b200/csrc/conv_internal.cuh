@@ -23,15 +23,16 @@ bool tc_fwd_supported(const dp_conv_desc* d);
 bool tc_dgrad_supported(const dp_conv_desc* d);
 bool tc_wgrad_supported(const dp_conv_desc* d);
 // writes BN partials when part != nullptr; *nparts receives the row count
+// fin != nullptr: the last CTA to retire also runs the BatchNorm finalisation over the partials (bn_fin.cuh)
 int tc_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, float* part, int* nparts,
-                cudaStream_t s);
+                cudaStream_t s, const dp_bn_fin* fin = nullptr);
 int tc_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
                   cudaStream_t s);
 // dgrad whose epilogue also accumulates sum(g'), sum(g' * yprev) per channel of dx (BatchNorm backward of the producer)
 bool tc_dgrad_bnstats_supported(const dp_conv_desc* d);
 int tc_conv_dgrad_bnstats(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
                           const void* yprev, const float* bn_scale_shift, float slope, float* part, int* nparts,
-                          cudaStream_t s);
+                          cudaStream_t s, const dp_bn_fin* fin = nullptr);
 // strided data gradient with every stride-parity class in one launch (class-packed weights, see conv_tc.cu)
 size_t tc_dgrad_classes_weight_elems(const dp_conv_desc* d);   // 0: not supported for this geometry
 int tc_pack_dgrad_classes(const dp_conv_desc* d, const float* w, void* out, cudaStream_t s);
@@ -42,7 +43,7 @@ int tc_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* d
 
 // same kernels over a strided / overlapping VIEW of x (element strides of w,h,t,b): the packed stem rows
 int tc_conv_fwd_view(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* w, void* y,
-                     float* part, int* nparts, cudaStream_t s);
+                     float* part, int* nparts, cudaStream_t s, const dp_bn_fin* fin = nullptr);
 int tc_conv_wgrad_view(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* dy, float* dw,
                        void* ws, size_t ws_bytes, cudaStream_t s);
 
@@ -52,6 +53,7 @@ int tc_conv_fwd_bnact(const dp_conv_desc* d, const long long* xstrides, const vo
                       float slope, const void* residual, float slope_res, void* z, cudaStream_t s);
 
 // BN partial statistics over a finished tensor (bn_act.cu)
-int bn_stats_launch(const void* y, int64_t rows, int Cp, int dtype, float* part, int* nparts, cudaStream_t s);
+int bn_stats_launch(const void* y, int64_t rows, int Cp, int dtype, float* part, int* nparts, cudaStream_t s,
+                    const dp_bn_fin* fin = nullptr);
 
 }  // namespace dp

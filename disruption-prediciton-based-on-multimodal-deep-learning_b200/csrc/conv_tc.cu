@@ -28,6 +28,7 @@
 #include "dp_common.cuh"
 #include "conv_internal.cuh"
 #include "tc_ptx.cuh"
+#include "bn_fin.cuh"
 #include <stdlib.h>
 #include <string.h>
 #include <mutex>
@@ -127,7 +128,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                       const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD1,
                       const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD3,
                       const __grid_constant__ TcParams p, const __nv_bfloat16* __restrict__ addend, float* __restrict__ part, long long* __restrict__ dbg,
-                      const __nv_bfloat16* __restrict__ yprev, const float* __restrict__ bn_ss) {
+                      const __nv_bfloat16* __restrict__ yprev, const float* __restrict__ bn_ss,
+                      const __grid_constant__ dp_bn_fin fin) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -826,12 +828,16 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   }
 
+  if (fin.kind) __threadfence();   // this CTA's row of `part` is visible device-wide before its ticket is taken
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+  // last CTA done: BatchNorm finalisation of the partials in this launch (no stand-alone finalize kernel); the pipeline
+  // stages are dead by now and lend their shared memory
+  if (fin.kind) bn_fin_tail(fin, part, reinterpret_cast<int*>(sm + 4096), reinterpret_cast<double*>(sm));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1269,7 +1275,8 @@ static GatherProblem class_problem(const dp_conv_desc* d, const ClassGeom& cg) {
 
 static int launch_gather(const GatherProblem& g, const void* src, const void* wgt, void* dst, const void* addend,
                          float* part, int* nparts, cudaStream_t s, const void* yprev = nullptr, const float* bn_ss = nullptr,
-                         float slope = 1.f, int epi_bn = 0, float slope_res = 1.f, const ClassGeom* cg = nullptr, int cpd = 0) {
+                         float slope = 1.f, int epi_bn = 0, float slope_res = 1.f, const ClassGeom* cg = nullptr, int cpd = 0,
+                         const dp_bn_fin* fin = nullptr) {
   TcPlan plan;
   const bool bwd_stats = yprev != nullptr;
   DP_REQUIRE(plan_gather(g, part != nullptr, &plan, bwd_stats, cg ? cpd : 0), DP_ERR_UNSUPPORTED, "tcgen05 conv: geometry not supported");
@@ -1337,7 +1344,7 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   cudaError_t attr_err = cudaSuccess;
   typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                          const CUtensorMap, const CUtensorMap, const TcParams, const __nv_bfloat16*, float*,
-                         long long*, const __nv_bfloat16*, const float*);
+                         long long*, const __nv_bfloat16*, const float*, const dp_bn_fin);
   static KernFn const kerns[20] = {tc_gather_gemm_kernel<0, 0, 1>, tc_gather_gemm_kernel<1, 1, 1>, tc_gather_gemm_kernel<2, 1, 1>,
                                    tc_gather_gemm_kernel<3, 1, 1>, tc_gather_gemm_kernel<1, 0, 1>, tc_gather_gemm_kernel<2, 0, 1>,
                                    tc_gather_gemm_kernel<3, 0, 1>, tc_gather_gemm_kernel<4, 0, 1>, tc_gather_gemm_kernel<5, 0, 1>,
@@ -1368,8 +1375,11 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
     DP_REQUIRE(!bwd_stats && p.drain_rs >= 1 && p.drain_rs <= (p.reg_stats ? 3 : 4), DP_ERR_UNSUPPORTED, "tcgen05 conv: no 256-pixel kernel for this shape");
     ki = p.reg_stats ? 12 + p.drain_rs : 15 + p.drain_rs;   // 13..15 / 16..19
   }
-  launch_pdl(kerns[ki], dim3(plan.grid), dim3(TC_THREADS), plan.smem, s, tmA, tmB, tmD, tmA2, tmB2, tmDk[1], tmDk[2], tmDk[3], p, (const __nv_bfloat16*)addend, part, dbg,
-             (const __nv_bfloat16*)yprev, bn_ss);
+  static const dp_bn_fin no_fin = {};
+  DP_REQUIRE(fin == nullptr || part != nullptr, DP_ERR_SHAPE, "tcgen05 conv: a fused finalisation needs the partials buffer");
+  const size_t smem = (fin && plan.smem < 8192) ? 8192 : plan.smem;   // the finalisation tail borrows 4 KB + a flag word
+  launch_pdl(kerns[ki], dim3(plan.grid), dim3(TC_THREADS), smem, s, tmA, tmB, tmD, tmA2, tmB2, tmDk[1], tmDk[2], tmDk[3], p, (const __nv_bfloat16*)addend, part, dbg,
+             (const __nv_bfloat16*)yprev, bn_ss, fin ? *fin : no_fin);
   if (getenv("DP_DEBUG_PLAN"))
     fprintf(stderr, "[tc_gather] dst %dx%dx%dx%d src C=%d taps=%d | tile bw=%d bh=%d bt=%d nloads=%d nsub=%d CB=%d ncblk=%d Ntile=%d MT=%d stages=%d lps=%d dual=%d CBt=%d stats=%d/%d stage_bytes=%d a_box=%d tiles=%d grid=%d\n",
             g.dT, g.dH, g.dW, g.dC, g.sC, g.kt * g.kh * g.kw, p.bw, p.bh, p.bt, p.nloads, p.nsub, p.CB, p.ncblk, p.Ntile, p.MT, p.num_stages, p.lps, p.dual_mma, p.CBt, p.reg_stats * 10 + p.drain_rs, p.mma_stats,
@@ -1455,8 +1465,8 @@ bool tc_dgrad_supported(const dp_conv_desc* d) {
 }
 
 int tc_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, float* part, int* nparts,
-                cudaStream_t s) {
-  return launch_gather(fwd_problem(d), x, w, y, nullptr, part, nparts, s);
+                cudaStream_t s, const dp_bn_fin* fin) {
+  return launch_gather(fwd_problem(d), x, w, y, nullptr, part, nparts, s, nullptr, nullptr, 1.f, 0, 1.f, nullptr, 0, fin);
 }
 
 bool tc_fwd_view_supported(const dp_conv_desc* d) { return tc_fwd_supported(d); }
@@ -1487,19 +1497,19 @@ bool tc_dgrad_bnstats_supported(const dp_conv_desc* d) {
 
 int tc_conv_dgrad_bnstats(const dp_conv_desc* d, const void* dy, const void* w, const void* addend, void* dx,
                           const void* yprev, const float* bn_scale_shift, float slope, float* part, int* nparts,
-                          cudaStream_t s) {
+                          cudaStream_t s, const dp_bn_fin* fin) {
   GatherProblem g;
   int ntaps = 0;
   DP_REQUIRE(d->st == 1 && d->sh == 1 && d->sw == 1 && dgrad_class(d, 0, 0, 0, &g, &ntaps) && ntaps > 0, DP_ERR_UNSUPPORTED,
              "tcgen05 dgrad+stats: stride-1 convolutions only");
-  return launch_gather(g, dy, w, dx, addend, part, nparts, s, yprev, bn_scale_shift, slope);
+  return launch_gather(g, dy, w, dx, addend, part, nparts, s, yprev, bn_scale_shift, slope, 0, 1.f, nullptr, 0, fin);
 }
 
 int tc_conv_fwd_view(const dp_conv_desc* d, const long long* xstrides, const void* x, const void* w, void* y,
-                     float* part, int* nparts, cudaStream_t s) {
+                     float* part, int* nparts, cudaStream_t s, const dp_bn_fin* fin) {
   GatherProblem g = fwd_problem(d);
   g.ss_w = xstrides[0]; g.ss_h = xstrides[1]; g.ss_t = xstrides[2]; g.ss_b = xstrides[3];
-  return launch_gather(g, x, w, y, nullptr, part, nparts, s);
+  return launch_gather(g, x, w, y, nullptr, part, nparts, s, nullptr, nullptr, 1.f, 0, 1.f, nullptr, 0, fin);
 }
 
 // ---- strided data gradient, all stride-parity classes in one launch ----

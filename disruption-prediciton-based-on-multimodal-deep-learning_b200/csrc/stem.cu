@@ -13,6 +13,7 @@
 // kernels, the weight packing and the C ABI.  The stem needs no data gradient (clips carry no grad).
 #include "dp_common.cuh"
 #include "conv_internal.cuh"
+#include "bn_fin.cuh"
 
 namespace dp {
 
@@ -149,6 +150,18 @@ DP_API int dp_stem_conv_fwd(const dp_conv_desc* d, const void* xp, const void* w
   long long xs[4];
   dp_conv_desc v = stem_view(d, xs);
   return tc_conv_fwd_view(&v, xs, xp, wv, y, part, nparts, as_stream(stream));
+}
+
+DP_API int dp_stem_conv_fwd_fin(const dp_conv_desc* d, const void* xp, const void* wv, void* y, float* part,
+                                const dp_bn_fin* fin, void* stream) {
+  DP_REQUIRE(stem_ok(d), DP_ERR_UNSUPPORTED, "stem path: geometry not covered");
+  DP_REQUIRE(xp && wv && y && part, DP_ERR_SHAPE, "dp_stem_conv_fwd_fin: NULL pointer");
+  const int rc = bn_fin_validate(fin, 1, d->Kp, "dp_stem_conv_fwd_fin");
+  if (rc != DP_OK) return rc;
+  long long xs[4];
+  dp_conv_desc v = stem_view(d, xs);
+  int nparts = 0;
+  return tc_conv_fwd_view(&v, xs, xp, wv, y, part, &nparts, as_stream(stream), fin);
 }
 
 DP_API int dp_stem_conv_fwd_bnact(const dp_conv_desc* d, const void* xp, const void* wv, const float* scale_shift, float slope,

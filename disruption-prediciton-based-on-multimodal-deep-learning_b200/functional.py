@@ -20,6 +20,12 @@ import torch
 from . import _lib as L
 
 _STATE = {"dtype": torch.bfloat16, "impl": L.IMPL_AUTO, "fuse_bn_reduce": True, "fuse_eval": True,
+          # experiment, off: BatchNorm finalisation by the last CTA of the kernel that produces the partial sums
+          # (dp_bn_fin) instead of stand-alone dp_bn_finalize / dp_bn_bwd_finalize launches.  64 launches less per step,
+          # but measured SLOWER (18.98 vs 18.35 ms/step): one CTA walks the 148-592 partial rows of all channel groups
+          # while 147 SMs idle (+15 us per conv, +26 us per reduction), the stand-alone kernels spread the groups over
+          # CTAs and cost ~5 us including the launch gap inside the CUDA graph.  DP_FUSE_FIN=1 enables it.
+          "fuse_fin": os.environ.get("DP_FUSE_FIN", "0") == "1",
           # experiment, off: weight gradients on a second stream.  Measured 18.97 vs 19.02 ms/step: the wgrad CTAs cannot
           # co-reside with the 384-thread gather CTAs and the BatchNorm passes already fill the machine.
           "wgrad_stream": os.environ.get("DP_WGRAD_STREAM", "0") == "1"}
@@ -239,6 +245,43 @@ def _zeros_ws(name: str, nbytes: int, device) -> torch.Tensor:
     return t
 
 
+_TICKETS = {}
+_N_TICKETS = 4096
+
+
+def _ticket(device) -> int:
+    """Address of a zero 32-bit word for a kernel with a "last CTA done" tail (dp_bn_fin.ticket).  The kernel re-arms
+    the word before it ends; the pool is handed out round-robin, far deeper than the launches one stream keeps in
+    flight, and a CUDA graph keeps the words it captured."""
+    key = device.index
+    pool = _TICKETS.get(key)
+    if pool is None:
+        pool = [torch.zeros(_N_TICKETS, dtype=torch.int32, device=device), 0]
+        _TICKETS[key] = pool
+    i = pool[1]
+    pool[1] = (i + 1) % _N_TICKETS
+    return pool[0].data_ptr() + 4 * i
+
+
+def _bn_fin_fwd(d, rows, gamma, beta, cfg, running_mean, running_var, stats, device) -> "L.BnFin":
+    return L.BnFin(kind=1, C=d.K, Cp=d.Kp, coef_zero=0, count=float(rows), gamma=gamma.data_ptr(), beta=beta.data_ptr(),
+                   eps=cfg.eps, momentum=cfg.momentum, running_mean=_p(running_mean), running_var=_p(running_var),
+                   mean=stats[0].data_ptr(), rstd=stats[1].data_ptr(), scale=stats[2].data_ptr(),
+                   shift=stats[3].data_ptr(), dgamma=None, dbeta=None, coef=None, ticket=_ticket(device))
+
+
+def _bn_fin_bwd(K, Kp, rows, stats, training, device):
+    """(fin, dgamma, dbeta, coef) for the backward sums of a layer with K (Kp padded) output channels."""
+    dgamma = torch.empty(K, dtype=torch.float32, device=device)
+    dbeta = torch.empty(K, dtype=torch.float32, device=device)
+    coef = torch.empty((2, Kp), dtype=torch.float32, device=device)
+    fin = L.BnFin(kind=2, C=K, Cp=Kp, coef_zero=0 if training else 1, count=float(rows), gamma=None, beta=None, eps=0.0,
+                  momentum=0.0, running_mean=None, running_var=None, mean=stats[0].data_ptr(), rstd=stats[1].data_ptr(),
+                  scale=None, shift=None, dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), coef=coef.data_ptr(),
+                  ticket=_ticket(device))
+    return fin, dgamma, dbeta, coef
+
+
 # ----------------------------------------------------------------------------------------------
 # layout
 # ----------------------------------------------------------------------------------------------
@@ -410,13 +453,24 @@ def layer_forward(x, weight, gamma, beta, running_mean, running_var, cfg: LayerC
         part = torch.empty((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=dev)
         nparts = C.c_int(0)
         t0 = _pb()
-        L.check(_conv_fwd_call(lib, geom, x, wf, y, part.data_ptr(), C.byref(nparts), impl, st), "dp_conv_fwd")
+        if _STATE["fuse_fin"]:
+            # BatchNorm finalisation (mean / rstd / scale / shift / running statistics) by the conv kernel's last CTA
+            fin = _bn_fin_fwd(d, geom.rows_out, gamma, beta, cfg, running_mean, running_var, stats, dev)
+            if geom.stem:
+                L.check(lib.dp_stem_conv_fwd_fin(C.byref(d), x.data_ptr(), wf.data_ptr(), y.data_ptr(), part.data_ptr(),
+                                                 C.byref(fin), st), "dp_stem_conv_fwd_fin")
+            else:
+                L.check(lib.dp_conv_fwd_fin(C.byref(d), x.data_ptr(), wf.data_ptr(), y.data_ptr(), part.data_ptr(),
+                                            C.byref(fin), impl, st), "dp_conv_fwd_fin")
+        else:
+            L.check(_conv_fwd_call(lib, geom, x, wf, y, part.data_ptr(), C.byref(nparts), impl, st), "dp_conv_fwd")
         if t0 is not None:
             _pe(t0, geom.families(impl)[1], geom.flops, geom.esize * (geom.rows_in * d.C + geom.rows_out * d.K))
-        L.check(lib.dp_bn_finalize(part.data_ptr(), nparts.value, d.K, d.Kp, float(geom.rows_out), gamma.data_ptr(),
-                                   beta.data_ptr(), cfg.eps, cfg.momentum, _p(running_mean), _p(running_var),
-                                   stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
-                                   st), "dp_bn_finalize")
+        if not _STATE["fuse_fin"]:
+            L.check(lib.dp_bn_finalize(part.data_ptr(), nparts.value, d.K, d.Kp, float(geom.rows_out), gamma.data_ptr(),
+                                       beta.data_ptr(), cfg.eps, cfg.momentum, _p(running_mean), _p(running_var),
+                                       stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
+                                       st), "dp_bn_finalize")
     else:
         if running_mean is None or running_var is None:
             raise L.DpError("eval-mode BatchNorm needs running statistics")
@@ -473,24 +527,37 @@ def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope
         raise L.DpError(f"grad {tuple(dz.shape)} {dz.dtype} does not match activation {tuple(y.shape)} {y.dtype}")
     mean, rstd, scale, shift = (stats[i].data_ptr() for i in range(4))
     elems = geom.esize * geom.rows_out * d.K
-    if pre_part is not None and out is None:
-        part, nparts = pre_part          # written by the consumer's data-gradient epilogue
+    fuse_fin = _STATE["fuse_fin"]
+    if pre_part is not None and out is None and len(pre_part) == 3:
+        dgamma, dbeta, coef = pre_part   # sums AND finalisation came out of the consumer's data-gradient launch
     else:
-        part = torch.empty((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=dev)
-        nparts = C.c_int(0)
-        t0 = _pb()
-        L.check(lib.dp_bn_act_bwd_reduce(dz.data_ptr(), y.data_ptr(), _p(out), scale, shift, mean, rstd, cfg.slope,
-                                         float(slope_res), part.data_ptr(), C.byref(nparts), geom.rows_out, d.Kp, d.dtype,
-                                         st), "dp_bn_act_bwd_reduce")
-        if t0 is not None:
-            _pe(t0, "bn_act_bwd_reduce", 0.0, elems * (3 if out is not None else 2))
-    dgamma = torch.empty(d.K, dtype=torch.float32, device=dev)
-    dbeta = torch.empty(d.K, dtype=torch.float32, device=dev)
-    coef = torch.empty((2, d.Kp), dtype=torch.float32, device=dev)
-    L.check(lib.dp_bn_bwd_finalize(part.data_ptr(), nparts.value, d.K, d.Kp, float(geom.rows_out), mean, rstd,
-                                   dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), st), "dp_bn_bwd_finalize")
-    if not training:
-        coef.zero_()  # eval-mode BN: statistics are constants, no mean/variance terms
+        if pre_part is not None and out is None:
+            part, nparts = pre_part          # written by the consumer's data-gradient epilogue
+            fused_here = False
+        else:
+            part = torch.empty((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=dev)
+            nparts = C.c_int(0)
+            t0 = _pb()
+            fused_here = fuse_fin
+            if fused_here:
+                fin, dgamma, dbeta, coef = _bn_fin_bwd(d.K, d.Kp, geom.rows_out, stats, training, dev)
+                L.check(lib.dp_bn_act_bwd_reduce_fin(dz.data_ptr(), y.data_ptr(), _p(out), scale, shift, cfg.slope,
+                                                     float(slope_res), part.data_ptr(), geom.rows_out, d.Kp, d.dtype,
+                                                     C.byref(fin), st), "dp_bn_act_bwd_reduce_fin")
+            else:
+                L.check(lib.dp_bn_act_bwd_reduce(dz.data_ptr(), y.data_ptr(), _p(out), scale, shift, mean, rstd, cfg.slope,
+                                                 float(slope_res), part.data_ptr(), C.byref(nparts), geom.rows_out, d.Kp,
+                                                 d.dtype, st), "dp_bn_act_bwd_reduce")
+            if t0 is not None:
+                _pe(t0, "bn_act_bwd_reduce", 0.0, elems * (3 if out is not None else 2))
+        if not fused_here:
+            dgamma = torch.empty(d.K, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(d.K, dtype=torch.float32, device=dev)
+            coef = torch.empty((2, d.Kp), dtype=torch.float32, device=dev)
+            L.check(lib.dp_bn_bwd_finalize(part.data_ptr(), nparts.value, d.K, d.Kp, float(geom.rows_out), mean, rstd,
+                                           dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), st), "dp_bn_bwd_finalize")
+            if not training:
+                coef.zero_()  # eval-mode BN: statistics are constants, no mean/variance terms
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if (want_dres and out is not None) else None
     t0 = _pb()
@@ -540,11 +607,20 @@ def layer_backward(saved, dz, weight_shape, cfg: LayerCfg, training: bool, slope
         if next_bn is not None:
             y_prev, stats_prev, slope_prev, box = next_bn
             npart = torch.empty((L.DP_MAX_PARTS, 2, d.Cp), dtype=torch.float32, device=dev)
-            nn_ = C.c_int(0)
-            L.check(lib.dp_conv_dgrad_bnstats(C.byref(d), dy.data_ptr(), wd.data_ptr(), _p(addend), dx.data_ptr(),
-                                              y_prev.data_ptr(), stats_prev[2].data_ptr(), float(slope_prev),
-                                              npart.data_ptr(), C.byref(nn_), impl, st), "dp_conv_dgrad_bnstats")
-            box.append((npart, nn_))
+            if fuse_fin:
+                # the producer's channels are this conv's input channels, its pixels this conv's input pixels
+                fin_p, dg_p, db_p, coef_p = _bn_fin_bwd(d.C, d.Cp, geom.rows_in, stats_prev, training, dev)
+                L.check(lib.dp_conv_dgrad_bnstats_fin(C.byref(d), dy.data_ptr(), wd.data_ptr(), _p(addend), dx.data_ptr(),
+                                                      y_prev.data_ptr(), stats_prev[2].data_ptr(), float(slope_prev),
+                                                      npart.data_ptr(), C.byref(fin_p), impl, st),
+                        "dp_conv_dgrad_bnstats_fin")
+                box.append((dg_p, db_p, coef_p))
+            else:
+                nn_ = C.c_int(0)
+                L.check(lib.dp_conv_dgrad_bnstats(C.byref(d), dy.data_ptr(), wd.data_ptr(), _p(addend), dx.data_ptr(),
+                                                  y_prev.data_ptr(), stats_prev[2].data_ptr(), float(slope_prev),
+                                                  npart.data_ptr(), C.byref(nn_), impl, st), "dp_conv_dgrad_bnstats")
+                box.append((npart, nn_))
         elif wd.dim() == 1:     # class-packed weights (pack_weights): every stride-parity class in one launch
             L.check(lib.dp_conv_dgrad_classes(C.byref(d), dy.data_ptr(), wd.data_ptr(), _p(addend), dx.data_ptr(), st),
                     "dp_conv_dgrad_classes")

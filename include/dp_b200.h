@@ -65,6 +65,35 @@ typedef struct dp_conv_desc {
   int32_t dtype; /* DP_F32 | DP_BF16: storage type of x, y, packed weights */
 } dp_conv_desc;
 
+/* "Last CTA done" BatchNorm finalisation, run inside the kernel that produces the per-CTA partial sums (dp_conv_fwd_fin,
+ * dp_stem_conv_fwd_fin, dp_conv_dgrad_bnstats_fin, dp_bn_act_bwd_reduce_fin) instead of a stand-alone dp_bn_finalize /
+ * dp_bn_bwd_finalize launch: 64 launches less per training step of the BASELINE model.
+ *   kind 1 (nn.BatchNorm3d, train mode, R2Plus1D.py:53-54): (sum y, sum y^2) -> mean, rstd, scale, shift written,
+ *           running_mean / running_var updated in place when non-NULL (momentum, unbiased variance);
+ *   kind 2 (its autograd): (sum g', sum g'*y) -> dbeta, dgamma (may be NULL), coef[2][Cp] = the two means dy needs;
+ *           mean / rstd are READ; coef_zero != 0 (eval-mode BatchNorm: constant statistics) writes coef = 0.
+ * ticket: one 32-bit word of device memory owned by the caller, zero on entry; the kernel leaves it zero.  A word must
+ * not be shared by two launches that can be in flight at the same time. */
+typedef struct dp_bn_fin {
+  int32_t kind;
+  int32_t C, Cp;
+  int32_t coef_zero;
+  double count;               /* elements per channel (B*T*H*W) */
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* running_mean;
+  float* running_var;
+  float* mean;
+  float* rstd;
+  float* scale;
+  float* shift;
+  float* dgamma;
+  float* dbeta;
+  float* coef;
+  unsigned int* ticket;
+} dp_bn_fin;
+
 int         dp_version(void);
 const char* dp_last_error(void);
 /* DP_OK iff the current device is compute capability 10.x (sm_100a code). */
@@ -138,6 +167,16 @@ int dp_conv_dgrad_classes(const dp_conv_desc* d, const void* dy, const void* w_c
 int dp_conv_dgrad_bnstats(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend,
                           void* dx, const void* y_prev, const float* scale_shift, float slope,
                           float* part, int* nparts, int impl, void* stream);
+/* dp_conv_fwd / dp_conv_dgrad_bnstats with the BatchNorm finalisation of the partials in the same launch (see
+ * dp_bn_fin): fin->kind 1 for the forward (the statistics of y = this layer's BatchNorm3d), kind 2 for the data
+ * gradient (the sums of the layer that produced x).  `part` is scratch for >= DP_MAX_PARTS * 2 * Kp (Cp) floats.  Where
+ * the partials do not come out of the tcgen05 epilogue (CUDA-core family, composed reductions) the finalisation runs in
+ * the last CTA of the reduction kernel instead; the result is the same. */
+int dp_conv_fwd_fin(const dp_conv_desc* d, const void* x, const void* w_fwd, void* y, float* part,
+                    const dp_bn_fin* fin, int impl, void* stream);
+int dp_conv_dgrad_bnstats_fin(const dp_conv_desc* d, const void* dy, const void* w_dgrad, const void* addend,
+                              void* dx, const void* y_prev, const float* scale_shift, float slope,
+                              float* part, const dp_bn_fin* fin, int impl, void* stream);
 size_t dp_conv_wgrad_workspace(const dp_conv_desc* d, int impl);
 /* dw (fp32, (K,C,kt,kh,kw)) = x^T * dy, deterministic split reduction through `workspace`. */
 int dp_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw,
@@ -155,6 +194,9 @@ int    dp_stem_pack_input_u8(const dp_conv_desc* d, const uint8_t* frames /* (B,
 int    dp_stem_pack_weights(const dp_conv_desc* d, const float* w, void* wv /* [Kp][kh][32] bf16 */, void* stream);
 int    dp_stem_conv_fwd(const dp_conv_desc* d, const void* xp, const void* wv, void* y, float* part, int* nparts,
                         void* stream);
+/* ... with the BatchNorm finalisation in the same launch (fin->kind 1, see dp_bn_fin / dp_conv_fwd_fin) */
+int    dp_stem_conv_fwd_fin(const dp_conv_desc* d, const void* xp, const void* wv, void* y, float* part,
+                            const dp_bn_fin* fin, void* stream);
 /* eval-mode stem: conv + BatchNorm(running statistics) + LeakyReLU in one kernel (see dp_conv_fwd_bnact) */
 int    dp_stem_conv_fwd_bnact(const dp_conv_desc* d, const void* xp, const void* wv, const float* scale_shift, float slope,
                               void* z, void* stream);
@@ -180,6 +222,10 @@ int dp_bn_act_bwd_reduce(const void* dz, const void* y, const void* out,
                          const float* scale, const float* shift, const float* mean,
                          const float* rstd, float slope, float slope_res,
                          float* part, int* nparts, int64_t rows, int Cp, int dtype, void* stream);
+/* pass 1 with dp_bn_bwd_finalize in the same launch (fin->kind 2: mean / rstd are taken from fin) */
+int dp_bn_act_bwd_reduce_fin(const void* dz, const void* y, const void* out, const float* scale, const float* shift,
+                             float slope, float slope_res, float* part, int64_t rows, int Cp, int dtype,
+                             const dp_bn_fin* fin, void* stream);
 /* dbeta = sum(g), dgamma = sum(g*xhat) = (sum(g*y) - mean*sum(g))*rstd (fp64), coef = {dbeta, dgamma}/count */
 int dp_bn_bwd_finalize(const float* part, int nparts, int C, int Cp, double count, const float* mean,
                        const float* rstd, float* dgamma, float* dbeta, float* coef, void* stream);

@@ -509,3 +509,164 @@ def test_conv_tcgen05_plan_variants(opts):
     finally:
         for k, v in defaults.items():
             L.set_option(k, v)
+
+
+def _fin_fwd(d, rows, gamma, beta, rm, rv, stats, ticket):
+    return L.BnFin(kind=1, C=d.K, Cp=d.Kp, coef_zero=0, count=float(rows), gamma=gamma.data_ptr(), beta=beta.data_ptr(),
+                   eps=1e-5, momentum=0.1, running_mean=rm.data_ptr(), running_var=rv.data_ptr(),
+                   mean=stats[0].data_ptr(), rstd=stats[1].data_ptr(), scale=stats[2].data_ptr(), shift=stats[3].data_ptr(),
+                   dgamma=None, dbeta=None, coef=None, ticket=ticket.data_ptr())
+
+
+@pytest.mark.parametrize("geom", [(45, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), 6, 16, 16),     # register statistics, one chunk pair
+                                  (32, 72, (1, 3, 3), (1, 1, 1), (0, 1, 1), 21, 64, 64),    # ... 80 channels, 148 CTAs, 256-pixel tiles
+                                  (64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), 4, 8, 8),      # CUDA-core statistics from the staged tile
+                                  (32, 115, (1, 3, 3), (1, 2, 2), (0, 1, 1), 4, 16, 16),    # statistics MMAs (Gram + ones)
+                                  (128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 4, 4)],    # two N tiles
+                         ids=lambda g: f"{g[0]}to{g[1]}_k{g[2]}_s{g[3]}_{g[5]}x{g[6]}")
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_conv_fwd_fused_finalize(geom, impl):
+    """dp_conv_fwd_fin (BatchNorm finalisation by the conv kernel's last CTA) == dp_conv_fwd + dp_bn_finalize, bit for
+    bit, in every statistics mode of the tcgen05 kernel and through the CUDA-core composition; the ticket word returns
+    to zero, so the same word serves the next launch."""
+    lib = L.load()
+    Cc, K, k, s, p, T, H, W = geom
+    big = H >= 64
+    B = 2 if big else 3
+    if big and impl == "simt":
+        pytest.skip("CUDA-core family at full resolution is covered by the small shapes")
+    dtype = torch.bfloat16
+    x, w = make_case(geom, B, dtype, 3)
+    xi = to_int(x, dtype)
+    gm = Fn.conv_geom(Cc, K, k, s, p, xi)
+    d = gm.desc
+    wf = torch.empty((d.Kp, gm.taps, d.Cp), dtype=dtype, device=DEV)
+    L.check(lib.dp_pack_weights(C.byref(d), w.contiguous().data_ptr(), wf.data_ptr(), None, L.stream_ptr()), "pack")
+    im = L.IMPL_TC if impl == "tc" else L.IMPL_SIMT
+    g = torch.Generator().manual_seed(4)
+    gamma = (torch.rand(K, generator=g) + 0.5).to(DEV)
+    beta = torch.randn(K, generator=g).to(DEV)
+    # reference: partials + stand-alone finalize
+    y0 = torch.empty(gm.out_shape, dtype=dtype, device=DEV)
+    part = torch.zeros((L.DP_MAX_PARTS, 2, d.Kp), dtype=torch.float32, device=DEV)
+    nparts = C.c_int(0)
+    L.check(lib.dp_conv_fwd(C.byref(d), xi.data_ptr(), wf.data_ptr(), y0.data_ptr(), part.data_ptr(), C.byref(nparts), im,
+                            L.stream_ptr()), "fwd")
+    st0 = torch.full((4, d.Kp), float("nan"), device=DEV)
+    rm0, rv0 = torch.zeros(K, device=DEV), torch.ones(K, device=DEV)
+    L.check(lib.dp_bn_finalize(part.data_ptr(), nparts.value, K, d.Kp, float(gm.rows_out), gamma.data_ptr(), beta.data_ptr(),
+                               1e-5, 0.1, rm0.data_ptr(), rv0.data_ptr(), st0[0].data_ptr(), st0[1].data_ptr(),
+                               st0[2].data_ptr(), st0[3].data_ptr(), L.stream_ptr()), "finalize")
+    ticket = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for rep in range(2):   # twice on the same ticket word
+        y1 = torch.empty_like(y0)
+        st1 = torch.full((4, d.Kp), float("nan"), device=DEV)
+        rm1, rv1 = torch.zeros(K, device=DEV), torch.ones(K, device=DEV)
+        part1 = torch.zeros_like(part)
+        fin = _fin_fwd(d, gm.rows_out, gamma, beta, rm1, rv1, st1, ticket)
+        L.check(lib.dp_conv_fwd_fin(C.byref(d), xi.data_ptr(), wf.data_ptr(), y1.data_ptr(), part1.data_ptr(), C.byref(fin),
+                                    im, L.stream_ptr()), "fwd_fin")
+        torch.cuda.synchronize()
+        assert int(ticket.item()) == 0
+        assert torch.equal(y0, y1)
+        assert torch.equal(st0, st1), (st0 - st1).abs().max()
+        assert torch.equal(rm0, rm1) and torch.equal(rv0, rv1)
+    # and the statistics themselves against fp64 on the bf16-rounded output
+    yf = from_int(y0, K).double()
+    mu = yf.mean(dim=(0, 2, 3, 4))
+    assert float((st0[0, :K].double() - mu).abs().max() / yf.abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("C_", [32, 72, 288])
+@pytest.mark.parametrize("with_out", [False, True])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_bwd_reduce_fused_finalize(C_, with_out, training):
+    """dp_bn_act_bwd_reduce_fin == dp_bn_act_bwd_reduce + dp_bn_bwd_finalize (bit for bit); coef_zero for eval-mode BN."""
+    lib = L.load()
+    Cp = Fn.ceil16(C_)
+    rows = 3 * 5 * 16 * 16
+    g = torch.Generator().manual_seed(8)
+    mk = lambda: (torch.randn(rows, Cp, generator=g).to(DEV) * (torch.arange(Cp, device=DEV) < C_)).bfloat16()
+    dz, y, out = mk(), mk(), mk()
+    ss = torch.zeros((4, Cp), device=DEV)          # mean, rstd, scale, shift
+    ss[0, :C_] = torch.randn(C_, generator=g).to(DEV) * 0.2
+    ss[1, :C_] = torch.rand(C_, generator=g).to(DEV) + 0.5
+    ss[2, :C_] = torch.rand(C_, generator=g).to(DEV) + 0.5
+    ss[3, :C_] = torch.randn(C_, generator=g).to(DEV) * 0.3
+    po = out.data_ptr() if with_out else None
+    part = torch.zeros((L.DP_MAX_PARTS, 2, Cp), dtype=torch.float32, device=DEV)
+    nparts = C.c_int(0)
+    L.check(lib.dp_bn_act_bwd_reduce(dz.data_ptr(), y.data_ptr(), po, ss[2].data_ptr(), ss[3].data_ptr(), ss[0].data_ptr(),
+                                     ss[1].data_ptr(), 0.01, 0.2, part.data_ptr(), C.byref(nparts), rows, Cp, L.DP_BF16,
+                                     L.stream_ptr()), "reduce")
+    dg0, db0, cf0 = torch.empty(C_, device=DEV), torch.empty(C_, device=DEV), torch.empty((2, Cp), device=DEV)
+    L.check(lib.dp_bn_bwd_finalize(part.data_ptr(), nparts.value, C_, Cp, float(rows), ss[0].data_ptr(), ss[1].data_ptr(),
+                                   dg0.data_ptr(), db0.data_ptr(), cf0.data_ptr(), L.stream_ptr()), "finalize")
+    if not training:
+        cf0.zero_()
+    ticket = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for rep in range(2):
+        dg1, db1 = torch.full((C_,), float("nan"), device=DEV), torch.full((C_,), float("nan"), device=DEV)
+        cf1 = torch.full((2, Cp), float("nan"), device=DEV)
+        part1 = torch.zeros_like(part)
+        fin = L.BnFin(kind=2, C=C_, Cp=Cp, coef_zero=0 if training else 1, count=float(rows), gamma=None, beta=None, eps=0.0,
+                      momentum=0.0, running_mean=None, running_var=None, mean=ss[0].data_ptr(), rstd=ss[1].data_ptr(),
+                      scale=None, shift=None, dgamma=dg1.data_ptr(), dbeta=db1.data_ptr(), coef=cf1.data_ptr(),
+                      ticket=ticket.data_ptr())
+        L.check(lib.dp_bn_act_bwd_reduce_fin(dz.data_ptr(), y.data_ptr(), po, ss[2].data_ptr(), ss[3].data_ptr(), 0.01, 0.2,
+                                             part1.data_ptr(), rows, Cp, L.DP_BF16, C.byref(fin), L.stream_ptr()), "reduce_fin")
+        torch.cuda.synchronize()
+        assert int(ticket.item()) == 0
+        assert torch.equal(dg0, dg1) and torch.equal(db0, db1) and torch.equal(cf0, cf1)
+
+
+@pytest.mark.parametrize("geom", [(72, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), 9, 16, 16),      # sums in the tcgen05 epilogue
+                                  (32, 72, (1, 3, 3), (1, 1, 1), (0, 1, 1), 5, 16, 16),
+                                  (32, 115, (1, 3, 3), (1, 2, 2), (0, 1, 1), 4, 16, 16)],    # composed: dgrad + reduction
+                         ids=lambda g: f"{g[0]}to{g[1]}_k{g[2]}_s{g[3]}")
+def test_dgrad_bnstats_fused_finalize(geom):
+    """dp_conv_dgrad_bnstats_fin == dp_conv_dgrad_bnstats + dp_bn_bwd_finalize of the producing layer (bit for bit)."""
+    lib = L.load()
+    B = 3
+    x, w = make_case(geom, B, torch.bfloat16, 5)
+    Cc, K, k, s, p, T, H, W = geom
+    xi = to_int(x, torch.bfloat16)
+    gm = Fn.conv_geom(Cc, K, k, s, p, xi)
+    d = gm.desc
+    wd = torch.empty((d.Cp, gm.taps, d.Kp), dtype=torch.bfloat16, device=DEV)
+    L.check(lib.dp_pack_weights(C.byref(d), w.contiguous().data_ptr(), None, wd.data_ptr(), L.stream_ptr()), "pack")
+    g = torch.Generator(device="cpu").manual_seed(12)
+    dyi = torch.randn(gm.out_shape, generator=g).to(DEV).bfloat16()
+    dyi[..., K:] = 0
+    yprev = torch.randn(xi.shape, generator=g).to(DEV).bfloat16()
+    yprev[..., Cc:] = 0
+    ss = torch.zeros((4, d.Cp), dtype=torch.float32, device=DEV)   # producer's mean, rstd, scale, shift
+    ss[0, :Cc] = torch.randn(Cc, generator=g).to(DEV) * 0.2
+    ss[1, :Cc] = torch.rand(Cc, generator=g).to(DEV) + 0.5
+    ss[2, :Cc] = torch.rand(Cc, generator=g).to(DEV) + 0.5
+    ss[3, :Cc] = torch.randn(Cc, generator=g).to(DEV) * 0.3
+    rows = gm.rows_in
+    dx0 = torch.empty_like(xi)
+    part = torch.zeros((L.DP_MAX_PARTS, 2, d.Cp), dtype=torch.float32, device=DEV)
+    nparts = C.c_int(0)
+    L.check(lib.dp_conv_dgrad_bnstats(C.byref(d), dyi.data_ptr(), wd.data_ptr(), None, dx0.data_ptr(), yprev.data_ptr(),
+                                      ss[2].data_ptr(), 0.01, part.data_ptr(), C.byref(nparts), L.IMPL_AUTO, L.stream_ptr()),
+            "dgrad_bnstats")
+    dg0, db0, cf0 = torch.empty(Cc, device=DEV), torch.empty(Cc, device=DEV), torch.empty((2, d.Cp), device=DEV)
+    L.check(lib.dp_bn_bwd_finalize(part.data_ptr(), nparts.value, Cc, d.Cp, float(rows), ss[0].data_ptr(), ss[1].data_ptr(),
+                                   dg0.data_ptr(), db0.data_ptr(), cf0.data_ptr(), L.stream_ptr()), "finalize")
+    ticket = torch.zeros(1, dtype=torch.int32, device=DEV)
+    dg1, db1 = torch.full((Cc,), float("nan"), device=DEV), torch.full((Cc,), float("nan"), device=DEV)
+    cf1 = torch.full((2, d.Cp), float("nan"), device=DEV)
+    dx1 = torch.empty_like(xi)
+    part1 = torch.zeros_like(part)
+    fin = L.BnFin(kind=2, C=Cc, Cp=d.Cp, coef_zero=0, count=float(rows), gamma=None, beta=None, eps=0.0, momentum=0.0,
+                  running_mean=None, running_var=None, mean=ss[0].data_ptr(), rstd=ss[1].data_ptr(), scale=None, shift=None,
+                  dgamma=dg1.data_ptr(), dbeta=db1.data_ptr(), coef=cf1.data_ptr(), ticket=ticket.data_ptr())
+    L.check(lib.dp_conv_dgrad_bnstats_fin(C.byref(d), dyi.data_ptr(), wd.data_ptr(), None, dx1.data_ptr(), yprev.data_ptr(),
+                                          ss[2].data_ptr(), 0.01, part1.data_ptr(), C.byref(fin), L.IMPL_AUTO, L.stream_ptr()),
+            "dgrad_bnstats_fin")
+    torch.cuda.synchronize()
+    assert int(ticket.item()) == 0
+    assert torch.equal(dx0, dx1)
+    assert torch.equal(dg0, dg1) and torch.equal(db0, db1) and torch.equal(cf0, cf1)
