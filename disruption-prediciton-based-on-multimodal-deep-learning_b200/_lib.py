@@ -60,6 +60,7 @@ SIGNATURES = {
     "dp_set_option": (_i, [C.c_char_p, _i]),
     "dp_get_option": (_i, [C.c_char_p]),
     "dp_set_debug_buffer": (_i, [_vp, _sz]),
+    "dp_conv_describe_plan": (_i, [_pdesc, _i, _i, C.c_char_p, _sz]),
     "dp_ncdhw_f32_to_ndhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dp_ndhwc_to_ncdhw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dp_u8_frames_to_ndhwc": (_i, [_vp, _vp, C.POINTER(C.c_float), _i, _i, _i, _i, _i, _i, _vp]),

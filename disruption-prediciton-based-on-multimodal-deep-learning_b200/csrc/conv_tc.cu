@@ -1599,6 +1599,28 @@ int tc_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const vo
   return DP_OK;
 }
 
+// development / test aid: the plan the tcgen05 gather kernel would run for a forward (op 0, with or without
+// BatchNorm statistics) or a stride-1 data gradient (op 1), as text -- no launch, works without a device
+int tc_describe_plan(const dp_conv_desc* d, int op, int has_stats, char* out, size_t n) {
+  GatherProblem g;
+  if (op == 0) {
+    g = fwd_problem(d);
+  } else {
+    int ntaps = 0;
+    if (!dgrad_class(d, 0, 0, 0, &g, &ntaps) || ntaps == 0) return DP_ERR_UNSUPPORTED;
+  }
+  TcPlan plan;
+  if (!plan_gather(g, has_stats != 0, &plan, op == 1 && has_stats != 0)) return DP_ERR_UNSUPPORTED;
+  const TcParams& p = plan.p;
+  snprintf(out, n,
+           "tile bw=%d bh=%d bt=%d MT=%d nloads=%d nsub=%d CB=%d ncblk=%d CBt=%d Ntile=%d n_ntiles=%d stages=%d lps=%d stage_bytes=%d "
+           "dual=%d acc_bufs=%d st_bufs=%d resident=%d reg_stats=%d mma_stats=%d drain_rs=%d tmem_cols=%d tiles=%d grid=%d smem=%zu",
+           p.bw, p.bh, p.bt, p.MT, p.nloads, p.nsub, p.CB, p.ncblk, p.CBt, p.Ntile, p.n_ntiles, p.num_stages, p.lps, p.stage_bytes,
+           p.dual_mma, p.acc_bufs, p.st_bufs, p.w_resident, p.reg_stats, p.mma_stats, p.drain_rs, p.tmem_cols, p.num_tiles, plan.grid,
+           plan.smem);
+  return DP_OK;
+}
+
 }  // namespace dp
 
 DP_API int dp_set_option(const char* name, int value) {
@@ -1608,6 +1630,10 @@ DP_API int dp_set_option(const char* name, int value) {
   if (dp::tc_option(name, value, true) >= 0 || dp::wg_option(name, value, true) >= 0) return DP_OK;
   dp::set_error("dp_set_option: unknown option '%s'", name);
   return DP_ERR_UNSUPPORTED;
+}
+DP_API int dp_conv_describe_plan(const dp_conv_desc* d, int op, int has_stats, char* out, size_t n) {
+  if (d == nullptr || out == nullptr || n == 0) return DP_ERR_SHAPE;
+  return dp::tc_describe_plan(d, op, has_stats, out, n);
 }
 DP_API int dp_get_option(const char* name) {
   if (name == nullptr) return -1;

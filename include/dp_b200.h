@@ -110,6 +110,9 @@ unsigned long long dp_simt_fallback_count(void);
  * "wg_enable", "wg_halo", "wg_stack", "pdl" (programmatic dependent launch of the hot kernels) */
 int         dp_set_option(const char* name, int value);
 int         dp_get_option(const char* name);
+/* development / test aid: the tile, pipeline and statistics plan of the tcgen05 gather kernel for a forward (op 0) or
+ * stride-1 data gradient (op 1) of this geometry, as one line of text (no launch; works without a device) */
+int         dp_conv_describe_plan(const dp_conv_desc* d, int op, int has_stats, char* out, size_t n);
 /* development aid: device buffer (>= 8 int64 per CTA) receiving per-role wait/busy cycle counters of the tcgen05
  * kernels; NULL switches it off (the default) */
 int         dp_set_debug_buffer(void* ptr, size_t bytes);

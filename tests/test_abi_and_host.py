@@ -273,3 +273,36 @@ def test_every_slowfast_conv_has_a_tcgen05_plan(golden_dir):
                              L.DP_BF16)
             for op in range(3):
                 assert lib.dp_conv_supported(C.byref(cg.desc), op, L.IMPL_TC), (B, g, op)
+
+
+def test_plans_of_the_heavy_layers_keep_their_pipeline_shape():
+    """dp_conv_describe_plan (no device needed): the five layers that carry 60 % of the step keep the pipeline features
+    their measured speed depends on -- 256-pixel tiles where they were faster, two MMA-issuing
+    warps, resident weights, statistics in epilogue registers, the narrow tail block of the 80-channel operands."""
+    import ctypes as C
+    from dp_b200 import _lib as L
+    from dp_b200 import functional as Fn
+
+    lib = L.load()
+
+    def plan(cin, cout, k, s, p, thw, op, stats):
+        T, H, W = thw
+        o = [(n + 2 * p[i] - k[i]) // s[i] + 1 for i, n in enumerate((T, H, W))]
+        d = L.ConvDesc(64, T, H, W, cin, Fn.ceil16(cin), *o, cout, Fn.ceil16(cout), *k, *s, *p, L.DP_BF16)
+        buf = C.create_string_buffer(512)
+        assert lib.dp_conv_describe_plan(C.byref(d), op, stats, buf, 512) == 0, (cin, cout, op)
+        return dict(kv.split("=") for kv in buf.value.decode().split() if "=" in kv)
+
+    full = (21, 64, 64)
+    t = plan(45, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), full, 0, 1)            # stem temporal forward
+    assert (t["MT"], t["dual"], t["reg_stats"], t["resident"], t["nloads"]) == ("2", "1", "1", "1", "1")
+    s = plan(32, 72, (1, 3, 3), (1, 1, 1), (0, 1, 1), full, 0, 1)            # conv2 spatial forward
+    assert (s["Ntile"], s["reg_stats"], s["resident"], s["nloads"], s["nsub"]) == ("80", "1", "1", "3", "3")
+    g = plan(32, 72, (1, 3, 3), (1, 1, 1), (0, 1, 1), full, 1, 0)            # conv2 spatial data gradient (80 -> 32)
+    assert (g["CBt"], g["dual"], g["acc_bufs"], g["resident"]) == ("16", "1", "4", "1")
+    u = plan(72, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), full, 1, 0)            # conv2 temporal data gradient (32 -> 80)
+    assert (u["MT"], u["dual"], u["st_bufs"]) == ("2", "1", "2")
+    for v in (t, s, g, u):
+        assert int(v["smem"]) <= 232448 and int(v["tmem_cols"]) <= 512 and v["grid"] == "148"
+    # the structure behind dp_bn_fin: 4 int32, a double, 2 pointers, 2 floats, 10 pointers
+    assert C.sizeof(L.BnFin) == 16 + 8 + 16 + 8 + 80
