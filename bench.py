@@ -133,7 +133,25 @@ class ClockSampler:
 # reference arm: the reference's own CPU implementation of the path (oracle port: the same torch CPU
 # primitives in the same order; /root/reference does not exist on the GPU box and has no installable package)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int, budget_s: float = 200.0):
+def cpu_model_name() -> str:
+    """`lscpu` model string of the host; /proc/cpuinfo when lscpu is missing."""
+    try:
+        out = subprocess.run(["lscpu"], capture_output=True, text=True, timeout=10).stdout
+        for l in out.splitlines():
+            if l.lower().startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except (OSError, subprocess.SubprocessError):
+        pass
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.lower().startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_reference_run(steps: int, warmup: int, budget_s: float = 200.0, anomaly_steps: int = 2):
     import torch
     from oracle import r2plus1d_port as port
 
@@ -161,7 +179,7 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float = 200.0):
         return time.perf_counter() - t0
 
     t_first = one(B)                       # also warms the allocator / thread pool
-    per_step_budget = budget_s / max(1, steps + warmup)
+    per_step_budget = budget_s / max(1, steps + warmup + anomaly_steps)
     while B > 1 and t_first * 0.9 > per_step_budget:
         B //= 2
         t_first = one(B)
@@ -169,8 +187,22 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float = 200.0):
         one(B)
     ts = [one(B) for _ in range(steps)]
     total = sum(ts)
-    return {"clips_per_s": B * steps / total, "ms_per_step": 1e3 * total / steps, "B": B, "cores": cores,
-            "steps": steps}
+    out = {"clips_per_s": B * steps / total, "ms_per_step": 1e3 * total / steps, "B": B, "cores": cores,
+           "steps": steps, "cpu_model": cpu_model_name(),
+           "clips_per_s_median": B / sorted(ts)[len(ts) // 2], "clips_per_s_best": B / min(ts)}
+    if anomaly_steps > 0:
+        # as shipped: src/train.py:15 switches autograd anomaly detection on globally at import
+        with torch.autograd.set_detect_anomaly(True):
+            ta = [one(B) for _ in range(anomaly_steps)]
+        out["clips_per_s_anomaly_on"] = B * len(ta) / sum(ta)
+    return out
+
+
+def cpu_baseline_block(r, sample: str):
+    return {"value": round(r["clips_per_s"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
+            "cpu_model": r["cpu_model"], "median": round(r["clips_per_s_median"], 3), "best": round(r["clips_per_s_best"], 3),
+            "anomaly_detection_on": None if "clips_per_s_anomaly_on" not in r else round(r["clips_per_s_anomaly_on"], 3),
+            "anomaly_note": "value/median/best: anomaly detection off (fair); anomaly_detection_on: as shipped (src/train.py:15)"}
 
 
 def run_reference_arm(args):
@@ -185,7 +217,7 @@ def run_reference_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "R2Plus1DClassifier((3,21,128,128),2,[1,2,2,1]) train step, Focal+DRW, CPU host cores",
                    "batch_per_step": r["B"]},
-        "cpu_baseline": {"value": r["clips_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "cpu_baseline": dict(cpu_baseline_block(r, sample), value=r["clips_per_s"]),
         "e2e": {"value": r["clips_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -486,9 +518,8 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(steps=3, warmup=1, budget_s=40.0)
-        cpu = {"value": round(r["clips_per_s"], 3), "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"B={r['B']} clips per step x 3 steps (after 1 warm-up) of the same model and step, fp32, "
-                         f"torch CPU primitives the reference calls (oracle/r2plus1d_port.py)"}
+        cpu = cpu_baseline_block(r, f"B={r['B']} clips per step x 3 steps (after 1 warm-up) of the same model and step, fp32, "
+                                    f"torch CPU primitives the reference calls (oracle/r2plus1d_port.py)")
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -53,6 +53,10 @@ json.dump({"source": f"{tag}_step_launches.csv", "families": {n: {"launches": a[
                                                               for n, a in fam.items()}},
           open(os.path.join(out, f"{tag}_dram_per_launch.json"), "w"), indent=1)
 raw = os.path.join(src, f"{tag}_prof_step_raw.csv")
+if not os.path.exists(raw) and os.path.exists(raw + ".gz"):
+    import gzip, shutil
+    with gzip.open(raw + ".gz", "rb") as fi, open(raw, "wb") as fo:
+        shutil.copyfileobj(fi, fo)
 if os.path.exists(raw):
     want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
