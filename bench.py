@@ -444,12 +444,16 @@ def run_ours(args):
         simt_launches = int(lib.dp_simt_launch_count() - sl0)
         simt_fallbacks = int(lib.dp_simt_fallback_count() - sf0)
 
-        if args.nvtx_step:    # one extra EAGER step inside an NVTX range: `ncu --nvtx --nvtx-include "dp_step/"` sees exactly one step
+        if args.nvtx_step:    # one extra EAGER step between cudaProfilerStart/Stop (and inside the NVTX range "dp_step"):
+            # `ncu --profile-from-start off` sees exactly one step, forward AND backward (the backward launches come from
+            # autograd's worker thread, which a thread-bound NVTX push/pop range filter silently drops)
             torch.cuda.synchronize()
+            torch.cuda.profiler.start()
             torch.cuda.nvtx.range_push("dp_step")
             step(x_dev[0], y_dev)
             torch.cuda.synchronize()
             torch.cuda.nvtx.range_pop()
+            torch.cuda.profiler.stop()
 
         # ---- per-kernel CUDA-event timing of the same step (roofline leg) ----
         kern = {}

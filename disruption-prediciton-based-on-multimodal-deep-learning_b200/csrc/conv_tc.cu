@@ -63,7 +63,14 @@ struct TcParams {
   int mma_stats, stat_M, acc_bufs;  // BN statistics accumulated in TMEM by the tensor core
   // staging tile (epilogue -> TMA store, and B operand of the statistics MMAs): chunks of cw channels, swizzled
   int cw_shift;  // log2(cw) for the chunked layout, -1 for one unswizzled chunk of Ntile channels
+  // a staging buffer holds ONE 128-row sub-tile; st_bufs of them form a ring (256-pixel tiles stage and store their two
+  // sub-tiles separately: the epilogue only waits for the store issued st_bufs SUB-tiles ago)
   int cw, st_chunks, st_rowbytes, st_chunk_bytes, st_buf_bytes, st_bufs, st_mask, st_layout;
+  int sub_ow, sub_oh, sub_ot;   // destination offset of the second sub-tile inside a 256-pixel tile
+  // 256-pixel tiles: 1 = every sub-tile is published to the store warp on its own (wide tiles: the epilogue of sub-tile
+  // j + st_bufs only waits for the store of sub-tile j), 0 = one hand-off per tile (narrow tiles, where a second
+  // fence / barrier / store-completion round per tile costs more than it hides: 164 vs 199 us on the 32-channel stem)
+  int pub_sub;
   int off_staging, off_ones, off_stats, off_scratch, off_bars;
   int tmem_cols, layout_type, sbo_bytes;
   int has_stats, has_addend;
@@ -111,7 +118,7 @@ struct TileIter {
 // phase) occupies its thread for ~180-230 cycles (scripts/ubench/sync_ops.cu).  mbarriers remain only where the
 // hardware requires them (TMA completion, tcgen05.commit), and the TMA pipeline moves `lps` loads per stage so that
 // one wait / one expect_tx / one commit covers a whole tile's worth of operands where shared memory allows.
-constexpr int BAR_SREADY = 3;   // +buf : epilogue (arrive) -> store warp (sync): staged tile complete
+constexpr int BAR_SREADY = 3;   // +buf (<= 4 ring slots) : epilogue (arrive) -> store warp (sync): staged sub-tile complete
 constexpr int BAR_TEMPTY = 7;   // +acc : epilogue (arrive) -> MMA warp (sync): TMEM accumulator drained
 constexpr int BAR_HANDOFF = TC_EPI + 32;
 
@@ -412,32 +419,41 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (STATS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     // ===================== TMA store warp: staged tile -> global, off the epilogue's critical path ==========
     const int nst = (p.Ntile + p.cw - 1) / p.cw;
-    const bool two_bufs = p.st_bufs == 2;
-    int it = 0;
+    const int R = p.st_bufs;
+    int it = 0, buf = 0;
+    uint32_t done = 0;   // sub-tiles whose store has read its staging buffer
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, ti.next()) {
-      const int buf = two_bufs ? (it & 1) : 0;
-      named_bar_sync(BAR_SREADY + buf, BAR_HANDOFF);
-      if (lane == 0) {
-        const uint32_t staging_s = sbase + (uint32_t)(p.off_staging + buf * p.st_buf_bytes);
-        for (int ch = 0; ch < nst && !(p.dbg_skip & 1); ++ch) {
-          int col = ti.n * p.Ntile + ch * p.cw;
-          const CUtensorMap* dmap = &tmD;
-          if (STATS == 0 && p.ncls > 1) {   // stride-parity classes: chunk -> (class view, channel within the class)
-            const int k = col / p.cpd;
-            col -= k * p.cpd;
-            dmap = k == 0 ? &tmD : (k == 1 ? &tmD1 : (k == 2 ? &tmD2 : &tmD3));
+      const bool per_tile = MT == 2 && !p.pub_sub;   // one hand-off for both sub-tiles (slots buf, buf + 1)
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        if (!per_tile || m == 0) named_bar_sync(BAR_SREADY + buf, BAR_HANDOFF);
+        if (lane == 0) {
+          const uint32_t staging_s = sbase + (uint32_t)(p.off_staging + buf * p.st_buf_bytes);
+          const int ow = ti.w * p.bw + (m ? p.sub_ow : 0), oh = ti.h * p.bh + (m ? p.sub_oh : 0), ot = ti.t * p.bt + (m ? p.sub_ot : 0);
+          for (int ch = 0; ch < nst && !(p.dbg_skip & 1); ++ch) {
+            int col = ti.n * p.Ntile + ch * p.cw;
+            const CUtensorMap* dmap = &tmD;
+            if (STATS == 0 && p.ncls > 1) {   // stride-parity classes: chunk -> (class view, channel within the class)
+              const int k = col / p.cpd;
+              col -= k * p.cpd;
+              dmap = k == 0 ? &tmD : (k == 1 ? &tmD1 : (k == 2 ? &tmD2 : &tmD3));
+            }
+            tma_store_5d(dmap, staging_s + (uint32_t)(ch * p.st_chunk_bytes), col, ow, oh, ot, ti.b);
           }
-          tma_store_5d(dmap, staging_s + (uint32_t)(ch * p.st_chunk_bytes), col, ti.w * p.bw, ti.h * p.bh, ti.t * p.bt, ti.b);
+          if (!per_tile || m == MT - 1) {
+            tma_store_commit();
+            tma_store_wait_read();   // the stores issued so far have finished reading their staging buffers
+            // publish "sub-tiles 0..done-1 have left their staging buffers": the epilogue warps poll this counter (a
+            // ~30-cycle shared-memory load) instead of meeting at a barrier, so they never wait for each other or for this warp
+            done += per_tile ? (uint32_t)MT : 1u;
+            st_release_shared(sfree_cnt, done);
+          }
         }
-        tma_store_commit();
-        tma_store_wait_read();   // this tile's store has finished reading its staging buffer
-        // publish "tiles 0..it have left their staging buffers": the epilogue warps poll this counter (a ~30-cycle
-        // shared-memory load) instead of meeting at a barrier, so they never wait for each other or for this warp
-        st_release_shared(sfree_cnt, (uint32_t)(it + 1));
+        __syncwarp();
+        if (++buf == R) buf = 0;
       }
-      __syncwarp();
     }
     if (lane == 0) tma_store_wait_all();
   } else if (warp >= 4) {
@@ -465,6 +481,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t st_mask = (uint32_t)p.st_mask;
     const bool legacy_stats = p.has_stats && !p.mma_stats && !STATS;
     const int st_bufs = p.st_bufs, bw_ = p.bw, bh_ = p.bh, bt_ = p.bt, dW_ = p.dW, dH_ = p.dH, dT_ = p.dT;
+    int sbuf = 0;          // ring slot of the next sub-tile to stage
+    uint32_t sub_idx = 0;  // sub-tiles staged so far
     int acc = 0;
     uint32_t acc_phase = 0;
     int it = 0;
@@ -483,7 +501,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, ti.next()) {
       const int n_idx = ti.n, b = ti.b;
-      const int buf = st_bufs == 2 ? (it & 1) : 0;
+      int buf = sbuf;   // (MT == 1: the tile's only slot; statistics readers below use it)
       uint8_t* staging = sm + p.off_staging + buf * p.st_buf_bytes;
       // per 128-row sub-tile: pixel coordinates, validity, row offset in the destination tensor
       bool valid_m[MT];
@@ -550,22 +568,31 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (edbg) w_tf += clock64() - c0;
       long long c1 = edbg ? clock64() : 0;
       tc_fence_after();
-      // the staging buffer is free once the TMA store issued st_bufs tiles ago has read it and (statistics MMAs) the
-      // MMAs over it have retired
-      if (it >= st_bufs) {
-        const uint32_t need = (uint32_t)(it - st_bufs + 1);
-        while (ld_acquire_shared(sfree_cnt) < need) {}
-        if (p.mma_stats) mbar_wait(sdone_bar(buf), (uint32_t)(((it / st_bufs) - 1) & 1));
-      }
       if (edbg) { const long long c2 = clock64(); w_a += c2 - c1; c1 = c2; }
 
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * MT * p.Ntile) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {   // not unrolled: one copy of the drain code for both sub-tiles
       {
+      // this sub-tile's ring slot is free once the TMA store issued st_bufs sub-tiles ago has read it and (statistics
+      // MMAs, MT == 1) the MMAs over it have retired
+      buf = sbuf;
+      staging = sm + p.off_staging + buf * p.st_buf_bytes;
+      // (one hand-off per tile: both slots are checked before the first sub-tile and published after the second)
+      const bool per_tile = MT == 2 && !p.pub_sub;
+      const uint32_t last = per_tile ? sub_idx + (uint32_t)(MT - 1) : sub_idx;   // newest sub-tile about to be overwritten
+      if ((!per_tile || m == 0) && last >= (uint32_t)st_bufs) {
+        const long long cw0_ = edbg ? clock64() : 0;
+        const uint32_t need = last - (uint32_t)st_bufs + 1u;
+        while (ld_acquire_shared(sfree_cnt) < need) {}
+        if (MT == 1 && p.mma_stats) mbar_wait(sdone_bar(buf), (uint32_t)(((it / st_bufs) - 1) & 1));
+        if (edbg) { const long long c2 = clock64(); w_a += c2 - cw0_; c1 += c2 - cw0_; }
+      }
+      ++sub_idx;
+      if (++sbuf == st_bufs) sbuf = 0;
       const bool valid = m ? valid_m[MT - 1] : valid_m[0];
       const __nv_bfloat16* arow = (STATS != 1 && p.has_addend && valid) ? addend + (m ? roff_m[MT - 1] : roff_m[0]) : nullptr;
-      const uint32_t row_off = (uint32_t)((e + 128 * m) * p.st_rowbytes);
+      const uint32_t row_off = (uint32_t)(e * p.st_rowbytes);
       const uint32_t taddr = taddr0 + (uint32_t)(m * p.Ntile);
       auto store16 = [&](const float* f, int c) {   // 16 consecutive channels starting at channel c of this tile
         uint4 o0, o1;
@@ -704,16 +731,22 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (rem >= 64) emit16(vb + 16, c0c + 48);
         }
       }
+      if (MT == 2 && (p.pub_sub || m == MT - 1)) {   // publish this sub-tile, or (narrow tiles) the pair: barrier of the first slot
+        fence_proxy_async_smem();
+        named_bar_arrive(BAR_SREADY + (p.pub_sub ? buf : buf - 1), BAR_HANDOFF);
+      }
       }   // m < MT
       }   // sub-tiles
       if (edbg) { const long long c2 = clock64(); w_b += c2 - c1; c1 = c2; }
       // accumulator drained: hand the TMEM buffer back to the MMA warp; publish the staged tile to the async proxy
       tc_fence_before();
       if (it + p.acc_bufs < my_tiles) named_bar_arrive(BAR_TEMPTY + acc, BAR_HANDOFF);
-      fence_proxy_async_smem();
-      if (legacy_stats) named_bar_sync(1, TC_EPI);
-      named_bar_arrive(BAR_SREADY + buf, BAR_HANDOFF);   // the TMA-store warp may read the tile
-      if (p.mma_stats) mbar_arrive(sready_bar(buf));     // ... and so may the statistics MMAs
+      if (MT == 1) {
+        fence_proxy_async_smem();
+        if (legacy_stats) named_bar_sync(1, TC_EPI);
+        named_bar_arrive(BAR_SREADY + buf, BAR_HANDOFF);   // the TMA-store warp may read the tile
+        if (p.mma_stats) mbar_arrive(sready_bar(buf));     // ... and so may the statistics MMAs
+      }
       if (edbg) { const long long c2 = clock64(); w_c += c2 - c1; c1 = c2; }
       if (legacy_stats) {
         // fallback (N tiles > 1): per-channel sum / sum of squares of the bf16 tile from the (unswizzled) staging tile
@@ -860,7 +893,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64, g_opt_mt = 0, g_opt_classes = 1;
+static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64, g_opt_mt = 0, g_opt_classes = 1, g_opt_pub_sub_min = 64, g_opt_fine_n = 48;
 int tc_option(const char* name, int value, bool set) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_opt_halo;
@@ -880,6 +913,8 @@ int tc_option(const char* name, int value, bool set) {
   else if (!strcmp(name, "tc_bwd_stats_max")) slot = &g_opt_bwd_stats_max;
   else if (!strcmp(name, "tc_mt")) slot = &g_opt_mt;
   else if (!strcmp(name, "tc_classes")) slot = &g_opt_classes;
+  else if (!strcmp(name, "tc_fine_n")) slot = &g_opt_fine_n;   // finest dual-issuer stages up to this many output channels
+  else if (!strcmp(name, "tc_pub_sub_min")) slot = &g_opt_pub_sub_min;   // 256-pixel tiles: per-sub-tile hand-off from this many channels
   if (slot == nullptr) return -1;
   if (set) *slot = value;
   return *slot;
@@ -978,7 +1013,7 @@ static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, 
   p.cw_shift = chunked ? (p.cw == 64 ? 6 : (p.cw == 32 ? 5 : 4)) : -1;
   p.stat_M = p.Ntile <= 64 ? 64 : 128;
   p.st_rowbytes = p.cw * 2;
-  p.st_chunk_bytes = round_up(PT * p.st_rowbytes, 1024);
+  p.st_chunk_bytes = round_up(128 * p.st_rowbytes, 1024);   // one staging buffer = one 128-row sub-tile
   p.st_chunks = (p.Ntile + p.cw - 1) / p.cw;
   if (p.mma_stats && p.st_chunks < p.stat_M / p.cw) p.st_chunks = p.stat_M / p.cw;   // the Gram A operand spans stat_M channels
   p.st_buf_bytes = p.st_chunks * p.st_chunk_bytes;
@@ -992,11 +1027,17 @@ static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, 
   p.w_resident = (g_opt_resident && p.n_ntiles == 1 && wgt_total <= (cls_cpd ? 131072 : 98304)) ? 1 : 0;
   const int stats_bytes = round_up(2 * g.dC * 4, 16);
   // the all-ones operand exists only for the statistics MMAs, the reduction scratch only with statistics
-  const int ones_bytes = p.mma_stats ? 2048 : 0, scratch_bytes = has_stats ? 16384 : 0;
+  // reduction scratch: the register statistics meet once at the end (4 row quadrants x Ntile x 2 floats); the staged-tile
+  // statistics keep 256 / (Ntile / 8) row groups per tile (16 KB); the statistics MMAs need none
+  const int ones_bytes = p.mma_stats ? 2048 : 0;
+  const int scratch_bytes = !has_stats ? 0 : (p.reg_stats ? round_up(32 * p.Ntile, 1024) : (p.mma_stats ? 0 : 16384));
   const int misc = ones_bytes + stats_bytes + scratch_bytes + 256 /*barriers*/ + 1024 /*alignment*/;
-  p.st_bufs = g_opt_st_bufs == 1 ? 1 : 2;
+  // ring of 128-row staging buffers: at least one per sub-tile of a tile; up to twice that (search below)
+  p.pub_sub = (MT == 2 && p.Ntile >= g_opt_pub_sub_min) ? 1 : 0;
+  const int st_min = MT, st_max = g_opt_st_bufs == 1 ? MT : 2 * MT;
+  p.st_bufs = st_min;
   auto fixed_bytes = [&]() { return p.st_bufs * p.st_buf_bytes + (p.w_resident ? wgt_total : 0) + misc; };
-  const int fixed = fixed_bytes();   // tile search budget (refined below)
+  const int fixed = fixed_bytes();   // tile search budget with the smallest ring (refined below)
 
   // tile / mode search
   double best = 1e30;
@@ -1021,7 +1062,7 @@ static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, 
         if (mode == 1) { rows_l = (bh + g.kh - 1) * bw; nloads = g.kw; nsub = g.kh; if (bh + g.kh - 1 > 256) continue; }
         if (mode == 2) { rows_l = (bt + g.kt - 1) * bh * bw; nloads = 1; nsub = g.kt; if (bt + g.kt - 1 > 256) continue; }
         const int stage = round_up(rows_l * rowbytes, 1024) + (p.w_resident ? 0 : nsub * p.b_sub_bytes);
-        if (fixed - p.st_buf_bytes + 2 * stage > TC_SMEM_MAX) continue;
+        if (fixed + 2 * stage > TC_SMEM_MAX) continue;
         const double ntiles = (double)((g.dW + bw - 1) / bw) * ((g.dH + bh - 1) / bh) * ((g.dT + bt - 1) / bt);
         const double cost = ntiles * ((double)nloads * p.ncblk * (rows_l * rowbytes + nsub * p.b_box_bytes) +
                                       0.15 * taps * (double)PT * g.sC * 2.0) - 1e-3 * bw;
@@ -1040,6 +1081,13 @@ static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, 
   p.num_tiles = (int)nt;
   p.dW = g.dW; p.dH = g.dH; p.dT = g.dT; p.dC = g.dC;
   p.mw = g.mw; p.mh = g.mh; p.mt = g.mt;
+  // second 128-row sub-tile of a 256-pixel tile (pixel order: w fastest, then h, then t): whole t slices, else h rows
+  p.sub_ow = p.sub_oh = p.sub_ot = 0;
+  if (MT == 2) {
+    if (p.bt > 1) p.sub_ot = p.bt / 2;
+    else if (p.bh > 1) p.sub_oh = p.bh / 2;
+    else p.sub_ow = p.bw / 2;
+  }
 
   int rows_l = PT;
   out->a_estride[0] = 1; out->a_estride[1] = g.mw; out->a_estride[2] = g.mh; out->a_estride[3] = g.mt; out->a_estride[4] = 1;
@@ -1103,19 +1151,33 @@ static bool plan_gather_mt(const GatherProblem& g, bool has_stats, TcPlan* out, 
       if (st < 2) continue;
       const int groups = (total_loads + lps - 1) / lps;
       const bool dual_ok = g_opt_dual && p.acc_bufs >= 2 && !p.mma_stats && st / 2 >= groups;
-      const long score = (dual_ok ? 1000000L : 0L) + ((st >= 3 || dual_ok) ? 100000L : 0L) + 100L * lps + st;
+      // within a tier a stage normally carries as many loads as fit (one mbarrier round per tile); the narrow, operand-bound
+      // tiles (N <= 48: 32 -> 80 channel dgrad, 72 -> 32 temporal conv) are load-latency bound instead and run 5-8 % faster
+      // with the FINEST stages that keep both issuers, because a slice is refilled as soon as its own MMAs retire
+      // (profiles/r2/r2p_layer_sweep.txt: 527 -> 487 us, 251 -> 239 us; the 80-channel forward loses 10 % the same way)
+      const long gran = (dual_ok && p.Ntile <= g_opt_fine_n) ? 100L * (17 - lps) : 100L * lps;
+      const long score = (dual_ok ? 1000000L : 0L) + ((st >= 3 || dual_ok) ? 100000L : 0L) + gran + st;
       if (score > best_score) { best_score = score; best_lps = lps; best_stages = st; }
     }
   };
-  search();
-  if (p.st_bufs == 2 && best_score < 1000000L) {   // a second staging buffer is worth less than two MMA warps / pipeline depth
-    const int keep_lps = best_lps, keep_st = best_stages;
-    const long keep_score = best_score;
-    p.st_bufs = 1;
-    search();
-    if (keep_lps != 0 && best_score / 100000L <= keep_score / 100000L) {   // keep two buffers unless one buys a better tier
-      p.st_bufs = 2; best_lps = keep_lps; best_stages = keep_st; best_score = keep_score;
+  // staging ring depth: start from the deepest ring and give slots back while that buys a better tier (two MMA warps >
+  // three stages > the rest): a second buffer per sub-tile is worth less than two issuers or pipeline depth, but the ring
+  // never goes below one slot per sub-tile, and 256-pixel tiles keep a third slot when it costs no tier
+  {
+    int keep_lps = 0, keep_st = 0, keep_bufs = 0;
+    long keep_score = -1;
+    for (int r = st_max; r >= st_min; --r) {
+      if (MT == 2 && !p.pub_sub && (r & 1)) continue;   // one hand-off per tile: the two slots of a tile are a pair
+      p.st_bufs = r;
+      search();
+      if (best_lps == 0) continue;
+      if (keep_lps == 0 || best_score / 100000L > keep_score / 100000L) {
+        keep_lps = best_lps; keep_st = best_stages; keep_bufs = r; keep_score = best_score;
+      }
+      if (keep_score >= 1000000L) break;   // two issuers already: deeper rings were tried first
     }
+    if (keep_lps != 0) { p.st_bufs = keep_bufs; best_lps = keep_lps; best_stages = keep_st; best_score = keep_score; }
+    else { p.st_bufs = st_min; best_lps = 0; }
   }
   if (best_lps == 0 && p.w_resident) {
     p.w_resident = 0;
@@ -1308,7 +1370,8 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
     rc = encode_wgt_map(&tmB2, wgt, taps * g.sC, g.dC, p.CBt, p.Ntile, swt);
     if (rc != DP_OK) return rc;
   }
-  const int dbox[5] = {p.cw, p.bw, p.bh, p.bt, 1};
+  // one TMA store moves one 128-row sub-tile
+  const int dbox[5] = {p.cw, p.sub_ow ? p.sub_ow : p.bw, p.sub_oh ? p.sub_oh : p.bh, p.sub_ot ? p.sub_ot : p.bt, 1};
   p.a_sw = (long long)g.vs_w * g.dC;
   p.a_sh = (long long)g.vs_h * g.FW * g.dC;
   p.a_st = (long long)g.vs_t * g.FH * g.FW * g.dC;
@@ -1614,9 +1677,9 @@ int tc_describe_plan(const dp_conv_desc* d, int op, int has_stats, char* out, si
   const TcParams& p = plan.p;
   snprintf(out, n,
            "tile bw=%d bh=%d bt=%d MT=%d nloads=%d nsub=%d CB=%d ncblk=%d CBt=%d Ntile=%d n_ntiles=%d stages=%d lps=%d stage_bytes=%d "
-           "dual=%d acc_bufs=%d st_bufs=%d resident=%d reg_stats=%d mma_stats=%d drain_rs=%d tmem_cols=%d tiles=%d grid=%d smem=%zu",
+           "dual=%d acc_bufs=%d st_bufs=%d pub_sub=%d resident=%d reg_stats=%d mma_stats=%d drain_rs=%d tmem_cols=%d tiles=%d grid=%d smem=%zu",
            p.bw, p.bh, p.bt, p.MT, p.nloads, p.nsub, p.CB, p.ncblk, p.CBt, p.Ntile, p.n_ntiles, p.num_stages, p.lps, p.stage_bytes,
-           p.dual_mma, p.acc_bufs, p.st_bufs, p.w_resident, p.reg_stats, p.mma_stats, p.drain_rs, p.tmem_cols, p.num_tiles, plan.grid,
+           p.dual_mma, p.acc_bufs, p.st_bufs, p.pub_sub, p.w_resident, p.reg_stats, p.mma_stats, p.drain_rs, p.tmem_cols, p.num_tiles, plan.grid,
            plan.smem);
   return DP_OK;
 }

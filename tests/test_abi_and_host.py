@@ -298,10 +298,11 @@ def test_plans_of_the_heavy_layers_keep_their_pipeline_shape():
     assert (t["MT"], t["dual"], t["reg_stats"], t["resident"], t["nloads"]) == ("2", "1", "1", "1", "1")
     s = plan(32, 72, (1, 3, 3), (1, 1, 1), (0, 1, 1), full, 0, 1)            # conv2 spatial forward
     assert (s["Ntile"], s["reg_stats"], s["resident"], s["nloads"], s["nsub"]) == ("80", "1", "1", "3", "3")
+    assert (s["MT"], s["dual"], s["st_bufs"]) == ("2", "1", "2")            # two issuers AND a slot per 128-row sub-tile
     g = plan(32, 72, (1, 3, 3), (1, 1, 1), (0, 1, 1), full, 1, 0)            # conv2 spatial data gradient (80 -> 32)
     assert (g["CBt"], g["dual"], g["acc_bufs"], g["resident"]) == ("16", "1", "4", "1")
     u = plan(72, 32, (3, 1, 1), (1, 1, 1), (1, 0, 0), full, 1, 0)            # conv2 temporal data gradient (32 -> 80)
-    assert (u["MT"], u["dual"], u["st_bufs"]) == ("2", "1", "2")
+    assert (u["MT"], u["dual"], u["st_bufs"]) == ("2", "1", "4")
     for v in (t, s, g, u):
         assert int(v["smem"]) <= 232448 and int(v["tmem_cols"]) <= 512 and v["grid"] == "148"
     # the structure behind dp_bn_fin: 4 int32, a double, 2 pointers, 2 floats, 10 pointers
