@@ -81,6 +81,7 @@ SIGNATURES = {
     "dp_stem_input_elems": (_sz, [_pdesc]),
     "dp_stem_pack_input_f32": (_i, [_pdesc, _vp, _vp, _vp]),
     "dp_stem_pack_input_u8": (_i, [_pdesc, _vp, C.POINTER(C.c_float), _vp, _vp]),
+    "dp_stem_weight_elems": (_sz, [_pdesc]),
     "dp_stem_pack_weights": (_i, [_pdesc, _vp, _vp, _vp]),
     "dp_stem_conv_fwd": (_i, [_pdesc, _vp, _vp, _vp, _vp, _pint, _vp]),
     "dp_stem_conv_fwd_fin": (_i, [_pdesc, _vp, _vp, _vp, _vp, _pfin, _vp]),

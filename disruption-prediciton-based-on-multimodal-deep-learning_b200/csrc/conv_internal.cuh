@@ -38,6 +38,7 @@ size_t tc_dgrad_classes_weight_elems(const dp_conv_desc* d);   // 0: not support
 int tc_pack_dgrad_classes(const dp_conv_desc* d, const float* w, void* out, cudaStream_t s);
 int tc_conv_dgrad_classes(const dp_conv_desc* d, const void* dy, const void* w_cls, const void* addend, void* dx, cudaStream_t s);
 size_t tc_wgrad_workspace(const dp_conv_desc* d);
+int tc_wgrad_describe(const dp_conv_desc* d, char* out, size_t n);   // the weight-gradient plan as text (no launch)
 int tc_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t s);
 

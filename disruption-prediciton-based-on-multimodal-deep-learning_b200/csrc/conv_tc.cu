@@ -1666,6 +1666,7 @@ int tc_conv_dgrad(const dp_conv_desc* d, const void* dy, const void* w, const vo
 // BatchNorm statistics) or a stride-1 data gradient (op 1), as text -- no launch, works without a device
 int tc_describe_plan(const dp_conv_desc* d, int op, int has_stats, char* out, size_t n) {
   GatherProblem g;
+  if (op == 2) return tc_wgrad_describe(d, out, n);
   if (op == 0) {
     g = fwd_problem(d);
   } else {

@@ -531,6 +531,17 @@ static bool split_halves(const dp_conv_desc* d, dp_conv_desc* h0, dp_conv_desc* 
   return true;
 }
 
+int tc_wgrad_describe(const dp_conv_desc* d, char* out, size_t n) {
+  WgPlan plan;
+  if (!plan_wgrad(d, &plan)) return DP_ERR_UNSUPPORTED;
+  const WgParams& p = plan.p;
+  snprintf(out, n, "tile bw=%d bh=%d bt=%d nloads=%d nsub=%d swap=%d stack=%d gpl=%d N=%d n_mt=%d n_tg=%d lpg=%d cbX=%d cbD=%d stages=%d "
+           "stage_bytes=%d xslot=%d dslot=%d nsplit=%d tiles_per_split=%d tmem_cols=%d grid=%d smem=%zu",
+           p.bw, p.bh, p.bt, p.nloads, p.nsub, p.swap, p.stack, p.gpl, p.N, p.n_mt, p.n_tg, p.lpg, p.cbX, p.cbD, p.num_stages, p.stage_bytes,
+           p.x_slot_bytes, p.d_slot_bytes, p.nsplit, p.tiles_per_split, p.tmem_cols, plan.grid, plan.smem);
+  return DP_OK;
+}
+
 bool tc_wgrad_supported(const dp_conv_desc* d) {
   if (d->dtype != DP_BF16) return false;
   WgPlan plan;

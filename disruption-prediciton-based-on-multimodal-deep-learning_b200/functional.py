@@ -401,7 +401,7 @@ def pack_weights(weight: torch.Tensor, geom: ConvGeom, dtype: torch.dtype, cache
     if weight.dtype != torch.float32 or not weight.is_contiguous():
         raise L.DpError("conv master weights must be contiguous float32")
     if geom.stem:
-        wf = torch.empty((d.Kp, d.kh, 32), dtype=torch.bfloat16, device=weight.device)
+        wf = torch.empty(int(L.load().dp_stem_weight_elems(C.byref(d))), dtype=torch.bfloat16, device=weight.device)
         wd = wf   # no data gradient on the stem path
         L.check(L.load().dp_stem_pack_weights(C.byref(d), weight.data_ptr(), wf.data_ptr(), L.stream_ptr()),
                 "dp_stem_pack_weights")

@@ -111,7 +111,8 @@ unsigned long long dp_simt_fallback_count(void);
 int         dp_set_option(const char* name, int value);
 int         dp_get_option(const char* name);
 /* development / test aid: the tile, pipeline and statistics plan of the tcgen05 gather kernel for a forward (op 0) or
- * stride-1 data gradient (op 1) of this geometry, as one line of text (no launch; works without a device) */
+ * stride-1 data gradient (op 1) of this geometry, or of the weight-gradient kernel (op 2), as one line of text (no
+ * launch; works without a device) */
 int         dp_conv_describe_plan(const dp_conv_desc* d, int op, int has_stats, char* out, size_t n);
 /* development aid: device buffer (>= 8 int64 per CTA) receiving per-role wait/busy cycle counters of the tcgen05
  * kernels; NULL switches it off (the default) */
@@ -186,15 +187,17 @@ int dp_conv_wgrad(const dp_conv_desc* d, const void* x, const void* dy, float* d
                   void* workspace, size_t workspace_bytes, int impl, void* stream);
 
 /* ---- stem fast path: C <= 4 input channels, kernel (1,kh,kw<=8), stride (1,sh,2), bf16 (R2Plus1D.py:137-140) ----
- * The clip is kept as packed rows XP[b][t][h][wp][4] (wp = w + pw, WP = 2*Wo + 6, zero padded) instead of
- * 16-channel NDHWC; forward and weight gradient run on the tcgen05 kernels over an overlapping-window view.
- * There is no data gradient on this path (clips carry no gradient). */
+ * The clip is kept as packed row pairs XP[b][t][P][wp][r][4] (padded row h + ph = 2P + r, wp = w + pw, zero padded;
+ * HP = Ho + ceil(kh/2) - 1, WP = 2*Wo + 6) instead of 16-channel NDHWC; forward and weight gradient run on the tcgen05
+ * kernels as a stride-1 (1,ceil(kh/2),1) convolution over an overlapping-window view with 64 "channels" (one halo box per
+ * tile).  Geometry: kt = 1, sh = sw = 2, kw <= 8, C <= 4.  There is no data gradient on this path (clips carry none). */
 int    dp_stem_supported(const dp_conv_desc* d);
 size_t dp_stem_input_elems(const dp_conv_desc* d);            /* bf16 elements of XP */
 int    dp_stem_pack_input_f32(const dp_conv_desc* d, const float* ncdhw, void* xp, void* stream);
 int    dp_stem_pack_input_u8(const dp_conv_desc* d, const uint8_t* frames /* (B,T,H,W,3) */, const float* mean3,
                              void* xp, void* stream);
-int    dp_stem_pack_weights(const dp_conv_desc* d, const float* w, void* wv /* [Kp][kh][32] bf16 */, void* stream);
+size_t dp_stem_weight_elems(const dp_conv_desc* d);           /* bf16 elements of wv */
+int    dp_stem_pack_weights(const dp_conv_desc* d, const float* w, void* wv /* [Kp][ceil(kh/2)][64] bf16 */, void* stream);
 int    dp_stem_conv_fwd(const dp_conv_desc* d, const void* xp, const void* wv, void* y, float* part, int* nparts,
                         void* stream);
 /* ... with the BatchNorm finalisation in the same launch (fin->kind 1, see dp_bn_fin / dp_conv_fwd_fin) */
