@@ -13,8 +13,32 @@ namespace dp {
 
 constexpr int RED_THREADS = 256;
 
+// 8 consecutive elements exactly as they sit in memory (4 registers for bf16): the reductions below issue the loads of
+// several rows BEFORE converting any of them, so that many rows are in flight per thread; a load that returns eight
+// converted floats (ld8) makes the compiler serialise rows for lack of registers (measured: 2-4 rows in flight, 81-85 %
+// of the copy rate for a read-only kernel)
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { uint4 u; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ Raw8<__nv_bfloat16> ld_raw8(const __nv_bfloat16* p) { Raw8<__nv_bfloat16> r; r.u = *reinterpret_cast<const uint4*>(p); return r; }
+__device__ __forceinline__ Raw8<float> ld_raw8(const float* p) {
+  Raw8<float> r; r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); return r;
+}
+__device__ __forceinline__ f8 cvt8(const Raw8<__nv_bfloat16>& x) {
+  f8 r;
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&x.u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y; }
+  return r;
+}
+__device__ __forceinline__ f8 cvt8(const Raw8<float>& x) {
+  f8 r;
+  r.v[0] = x.a.x; r.v[1] = x.a.y; r.v[2] = x.a.z; r.v[3] = x.a.w; r.v[4] = x.b.x; r.v[5] = x.b.y; r.v[6] = x.b.z; r.v[7] = x.b.w;
+  return r;
+}
+
 // ---- generic per-channel column reduction of two quantities over [rows][Cp] ----
-// F: __device__ void operator()(int64_t elem_offset, int c0, float* a8, float* b8) accumulates 8 channels
+// F: Raw load(int64_t elem_offset) fetches one 8-channel vector of every input stream; acc(raw, a8, b8) accumulates it
 template <typename F>
 __global__ void __launch_bounds__(RED_THREADS, 2)
 col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part, const dp_bn_fin fin) {  // f by value: per-thread register copy
@@ -36,17 +60,15 @@ col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part, const dp
     const int cv = tid % vpr, rl = tid / vpr;
     f.init(cv * 8);                       // this thread's 8 channels never change: parameters live in registers
     int64_t r = r0 + rl;
-    for (; r + 7 * rpi < r1; r += 8 * rpi) {  // eight independent rows in flight (two CTAs of 256 threads per SM)
+    constexpr int U = F::kRowsInFlight;       // rows in flight per thread (two CTAs of 256 threads per SM)
+    for (; r + (U - 1) * rpi < r1; r += U * rpi) {
+      typename F::Raw raw[U];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) f((r + u * rpi) * Cp + cv * 8, a, b);
+      for (int u = 0; u < U; ++u) raw[u] = f.load((r + u * rpi) * Cp + cv * 8);
+#pragma unroll
+      for (int u = 0; u < U; ++u) f.acc(raw[u], a, b);   // same order as row-by-row: the sums do not change
     }
-    for (; r + 3 * rpi < r1; r += 4 * rpi) {
-      f(r * Cp + cv * 8, a, b);
-      f((r + rpi) * Cp + cv * 8, a, b);
-      f((r + 2 * rpi) * Cp + cv * 8, a, b);
-      f((r + 3 * rpi) * Cp + cv * 8, a, b);
-    }
-    for (; r < r1; r += rpi) f(r * Cp + cv * 8, a, b);
+    for (; r < r1; r += rpi) f.acc(f.load(r * Cp + cv * 8), a, b);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[0][tid * 8 + j] = a[j]; red[1][tid * 8 + j] = b[j]; }
@@ -65,9 +87,12 @@ col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part, const dp
   }
 }
 
+// one wave of two CTAs per SM: with 8 rows x 2 streams in flight per thread that saturates HBM, and the finalize kernel
+// behind it reads half the partial rows of the former four CTAs per SM
 static int reduce_grid(int64_t rows) {
   int64_t g = (rows + 63) / 64;
-  if (g > DP_MAX_PARTS) g = DP_MAX_PARTS;
+  const int64_t cap = 2 * (int64_t)num_sms() < DP_MAX_PARTS ? 2 * (int64_t)num_sms() : DP_MAX_PARTS;
+  if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
 }
@@ -75,34 +100,45 @@ static int reduce_grid(int64_t rows) {
 template <typename T>
 struct StatsF {
   const T* y;
+  struct Raw { Raw8<T> v; };
+  static constexpr int kRowsInFlight = sizeof(T) == 2 ? 16 : 8;
   __device__ __forceinline__ void init(int) {}
-  __device__ __forceinline__ void operator()(int64_t off, float* a, float* b) const {
-    const f8 v = ld8(y + off);
+  __device__ __forceinline__ Raw load(int64_t off) const { Raw r; r.v = ld_raw8(y + off); return r; }
+  __device__ __forceinline__ void acc(const Raw& r, float* a, float* b) const {
+    const f8 v = cvt8(r.v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a[j] += v.v[j]; b[j] = fmaf(v.v[j], v.v[j], b[j]); }
   }
 };
 
-template <typename T>
+template <typename T, bool HAS_OUT>   // HAS_OUT: a third stream (the block output behind a residual add + activation)
 struct BwdReduceF {
   const T* dz; const T* y; const T* out;
   const float* scale; const float* shift; const float* mean; const float* rstd;
   float slope, slope_res;
   float r_scale[8], r_shift[8];
+  struct Raw { Raw8<T> g, v, o; };   // (o stays dead without the third stream)
+  static constexpr int kRowsInFlight = sizeof(T) == 2 ? (HAS_OUT ? 5 : 8) : (HAS_OUT ? 2 : 4);
   // accumulates sum(g) and sum(g*y) with the RAW conv output y; bn_bwd_finalize turns the second into
   // sum(g*xhat) = (sum(g*y) - mean*sum(g)) * rstd in fp64, so the streaming loop needs two parameters per channel
   __device__ __forceinline__ void init(int c0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { r_scale[j] = scale[c0 + j]; r_shift[j] = shift[c0 + j]; }
   }
-  __device__ __forceinline__ void operator()(int64_t off, float* a, float* b) const {
-    const f8 g = ld8(dz + off), v = ld8(y + off);
+  __device__ __forceinline__ Raw load(int64_t off) const {
+    Raw r;
+    r.g = ld_raw8(dz + off); r.v = ld_raw8(y + off);
+    if (HAS_OUT) r.o = ld_raw8(out + off);
+    return r;
+  }
+  __device__ __forceinline__ void acc(const Raw& r, float* a, float* b) const {
+    const f8 g = cvt8(r.g), v = cvt8(r.v);
     f8 o;
-    if (out != nullptr) o = ld8(out + off);
+    if (HAS_OUT) o = cvt8(r.o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float gg = g.v[j];
-      if (out != nullptr) gg *= (o.v[j] > 0.f ? 1.f : slope_res);
+      if (HAS_OUT) gg *= (o.v[j] > 0.f ? 1.f : slope_res);
       const float u = fmaf(v.v[j], r_scale[j], r_shift[j]);
       gg *= (u > 0.f ? 1.f : slope);
       a[j] += gg;
@@ -131,7 +167,7 @@ int bn_stats_launch(const void* y, int64_t rows, int Cp, int dtype, float* part,
 }
 
 // ---- finalize: partials -> mean/rstd/scale/shift, running stats (momentum, unbiased var) ----
-// One CTA of 256 threads per 32 channels (bn_fin.cuh: 8 part-lanes x 32 channel-lanes, fp64 partial sums combined in a
+// One CTA of 256 threads per 16 channels (bn_fin.cuh: 16 part-lanes x 16 channel-lanes, fp64 partial sums combined in a
 // fixed order, reads coalesced along the channel dimension).  The producing kernels run the same code in their last
 // CTA when they are given a dp_bn_fin; these stand-alone launches serve partials that come without one.
 __global__ void __launch_bounds__(FIN_CH * FIN_PL)
@@ -156,7 +192,8 @@ __global__ void bn_eval_coeffs_kernel(const float* rm, const float* rv, const fl
 // ---- elementwise passes ----
 // Grid-stride loops whose stride is a multiple of the vectors-per-row, so a thread always works on the same
 // 8 channels and keeps their parameters in registers (no per-element parameter traffic).
-template <typename T>
+// V vectors in flight per thread: the raw 16-byte loads of all V are issued before any is converted (see Raw8)
+template <typename T, bool HAS_RES, int V>
 __global__ void __launch_bounds__(256)
 bn_act_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                     float slope, const T* __restrict__ residual, float slope_res, T* __restrict__ z,
@@ -172,34 +209,37 @@ bn_act_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, co
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
-  auto one = [&](const f8& a_in, const f8& r, int64_t v) {
-    f8 a = a_in;
+  auto one = [&](const Raw8<T>& ya, const Raw8<T>& ra, int64_t v) {
+    f8 a = cvt8(ya), r;
+    if (HAS_RES) r = cvt8(ra);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float u = lrelu(fmaf(a.v[j], sc[j], sh[j]), slope);
-      if (residual != nullptr) u = lrelu(u + r.v[j], slope_res);
+      if (HAS_RES) u = lrelu(u + r.v[j], slope_res);
       a.v[j] = u;
     }
     st8(z + v * 8, a);
   };
   int64_t v = v0;
-  for (; v + stride < nvec; v += 2 * stride) {   // two independent vectors in flight per thread
-    const f8 a0 = ld8(y + v * 8), a1 = ld8(y + (v + stride) * 8);
-    f8 r0, r1;
-    if (residual != nullptr) { r0 = ld8(residual + v * 8); r1 = ld8(residual + (v + stride) * 8); }
-    one(a0, r0, v);
-    one(a1, r1, v + stride);
+  for (; v + (V - 1) * stride < nvec; v += V * stride) {
+    Raw8<T> ya[V], ra[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      ya[u] = ld_raw8(y + (v + u * stride) * 8);
+      if (HAS_RES) ra[u] = ld_raw8(residual + (v + u * stride) * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < V; ++u) one(ya[u], ra[u], v + u * stride);
   }
-  if (v < nvec) {
-    const f8 a0 = ld8(y + v * 8);
-    f8 r0;
-    if (residual != nullptr) r0 = ld8(residual + v * 8);
-    one(a0, r0, v);
+  for (; v < nvec; v += stride) {
+    Raw8<T> ya = ld_raw8(y + v * 8), ra;
+    if (HAS_RES) ra = ld_raw8(residual + v * 8);
+    one(ya, ra, v);
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+template <typename T, bool HAS_OUT, int V>
+__global__ void __launch_bounds__(256, 4)   // 64 registers: four CTAs per SM
 bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y, const T* __restrict__ out,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -223,21 +263,38 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y, const
     kb[j] = -sc[j] * c1r;
     ka[j] = -sc[j] * (coef[c] - mean[c] * c1r);
   }
-  for (int64_t v = v0; v < nvec; v += stride) {
-    const f8 g = ld8(dz + v * 8), yy = ld8(y + v * 8);
+  auto one = [&](const Raw8<T>& gr, const Raw8<T>& yr, const Raw8<T>& orr, int64_t v) {
+    const f8 g = cvt8(gr), yy = cvt8(yr);
     f8 o, res, d;
-    if (out != nullptr) o = ld8(out + v * 8);
+    if (HAS_OUT) o = cvt8(orr);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float gg = g.v[j];
-      if (out != nullptr) gg *= (o.v[j] > 0.f ? 1.f : slope_res);
+      if (HAS_OUT) gg *= (o.v[j] > 0.f ? 1.f : slope_res);
       res.v[j] = gg;
       const float u = fmaf(yy.v[j], sc[j], sh[j]);
       gg *= (u > 0.f ? 1.f : slope);
       d.v[j] = fmaf(sc[j], gg, fmaf(kb[j], yy.v[j], ka[j]));
     }
     st8(dy + v * 8, d);
-    if (dres != nullptr) st8(dres + v * 8, res);
+    if (HAS_OUT && dres != nullptr) st8(dres + v * 8, res);
+  };
+  int64_t v = v0;
+  for (; v + (V - 1) * stride < nvec; v += V * stride) {
+    Raw8<T> gr[V], yr[V], orr[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      gr[u] = ld_raw8(dz + (v + u * stride) * 8);
+      yr[u] = ld_raw8(y + (v + u * stride) * 8);
+      if (HAS_OUT) orr[u] = ld_raw8(out + (v + u * stride) * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < V; ++u) one(gr[u], yr[u], orr[u], v + u * stride);
+  }
+  for (; v < nvec; v += stride) {
+    Raw8<T> gr = ld_raw8(dz + v * 8), yr = ld_raw8(y + v * 8), orr;
+    if (HAS_OUT) orr = ld_raw8(out + v * 8);
+    one(gr, yr, orr, v);
   }
 }
 
@@ -304,14 +361,16 @@ DP_API int dp_bn_act_apply(const void* y, const float* scale, const float* shift
   const int64_t nvec = rows * (Cp / 8);
   const int grid = ew_grid(nvec, Cp / 8);
   const size_t sm = 0;
-  if (dtype == DP_BF16)
-    launch_pdl(bn_act_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(256), sm, as_stream(stream),
-               (const __nv_bfloat16*)y, scale, shift, slope, (const __nv_bfloat16*)residual, slope_res, (__nv_bfloat16*)z,
-               nvec, Cp);
-  else
-    bn_act_apply_kernel<float><<<grid, 256, sm, as_stream(stream)>>>((const float*)y, scale, shift, slope,
-                                                                     (const float*)residual, slope_res, (float*)z,
-                                                                     nvec, Cp);
+  cudaStream_t st_ = as_stream(stream);
+#define DP_APPLY_LAUNCH(T, RES, V)                                                                                    \
+  launch_pdl(bn_act_apply_kernel<T, RES, V>, dim3(grid), dim3(256), sm, st_, (const T*)y, scale, shift, slope,        \
+             (const T*)residual, slope_res, (T*)z, nvec, Cp)
+  if (dtype == DP_BF16) {
+    if (residual != nullptr) DP_APPLY_LAUNCH(__nv_bfloat16, true, 2); else DP_APPLY_LAUNCH(__nv_bfloat16, false, 4);
+  } else {
+    if (residual != nullptr) DP_APPLY_LAUNCH(float, true, 1); else DP_APPLY_LAUNCH(float, false, 2);
+  }
+#undef DP_APPLY_LAUNCH
   return check_launch("dp_bn_act_apply");
 }
 
@@ -324,13 +383,23 @@ static int bwd_reduce_launch(const void* dz, const void* y, const void* out, con
   cudaStream_t s = as_stream(stream);
   const dp_bn_fin f_ = fin ? *fin : kNoFin;
   if (dtype == DP_BF16) {
-    BwdReduceF<__nv_bfloat16> f{(const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, (const __nv_bfloat16*)out,
-                                scale, shift, mean, rstd, slope, slope_res};
-    launch_pdl(col_reduce2_kernel<BwdReduceF<__nv_bfloat16>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+    if (out != nullptr) {
+      BwdReduceF<__nv_bfloat16, true> f{(const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, (const __nv_bfloat16*)out,
+                                        scale, shift, mean, rstd, slope, slope_res};
+      launch_pdl(col_reduce2_kernel<BwdReduceF<__nv_bfloat16, true>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+    } else {
+      BwdReduceF<__nv_bfloat16, false> f{(const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, nullptr,
+                                         scale, shift, mean, rstd, slope, slope_res};
+      launch_pdl(col_reduce2_kernel<BwdReduceF<__nv_bfloat16, false>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+    }
   } else {
-    BwdReduceF<float> f{(const float*)dz, (const float*)y, (const float*)out, scale, shift, mean, rstd, slope,
-                        slope_res};
-    launch_pdl(col_reduce2_kernel<BwdReduceF<float>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+    if (out != nullptr) {
+      BwdReduceF<float, true> f{(const float*)dz, (const float*)y, (const float*)out, scale, shift, mean, rstd, slope, slope_res};
+      launch_pdl(col_reduce2_kernel<BwdReduceF<float, true>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+    } else {
+      BwdReduceF<float, false> f{(const float*)dz, (const float*)y, nullptr, scale, shift, mean, rstd, slope, slope_res};
+      launch_pdl(col_reduce2_kernel<BwdReduceF<float, false>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+    }
   }
   if (nparts != nullptr) *nparts = grid;
   return check_launch(who);
@@ -377,14 +446,16 @@ DP_API int dp_bn_act_bwd_apply(const void* dz, const void* y, const void* out, c
   const int64_t nvec = rows * (Cp / 8);
   const int grid = ew_grid(nvec, Cp / 8);
   const size_t sm = 0;
-  if (dtype == DP_BF16)
-    launch_pdl(bn_act_bwd_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(256), sm, as_stream(stream),
-               (const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, (const __nv_bfloat16*)out, scale, shift, mean, rstd, coef,
-               slope, slope_res, (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, nvec, Cp);
-  else
-    bn_act_bwd_apply_kernel<float><<<grid, 256, sm, as_stream(stream)>>>(
-        (const float*)dz, (const float*)y, (const float*)out, scale, shift, mean, rstd, coef, slope, slope_res,
-        (float*)dy, (float*)dres, nvec, Cp);
+  cudaStream_t st_ = as_stream(stream);
+#define DP_BWD_APPLY_LAUNCH(T, OUT, V)                                                                                \
+  launch_pdl(bn_act_bwd_apply_kernel<T, OUT, V>, dim3(grid), dim3(256), sm, st_, (const T*)dz, (const T*)y,           \
+             (const T*)out, scale, shift, mean, rstd, coef, slope, slope_res, (T*)dy, (T*)dres, nvec, Cp)
+  if (dtype == DP_BF16) {
+    if (out != nullptr) DP_BWD_APPLY_LAUNCH(__nv_bfloat16, true, 1); else DP_BWD_APPLY_LAUNCH(__nv_bfloat16, false, 2);
+  } else {
+    if (out != nullptr) DP_BWD_APPLY_LAUNCH(float, true, 1); else DP_BWD_APPLY_LAUNCH(float, false, 1);
+  }
+#undef DP_BWD_APPLY_LAUNCH
   return check_launch("dp_bn_act_bwd_apply");
 }
 

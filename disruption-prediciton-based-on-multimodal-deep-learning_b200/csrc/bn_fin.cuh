@@ -14,9 +14,11 @@
 
 namespace dp {
 
-constexpr int FIN_CH = 32, FIN_PL = 8;   // one group = 32 channels x 8 part-lanes = 256 threads
+// one group = 16 channels x 16 part-lanes = 256 threads: the finalize kernels are pure load latency on the critical path
+// between every conv and its apply pass, so the partial rows are spread over as many threads as the CTA has
+constexpr int FIN_CH = 16, FIN_PL = 16;
 
-// Threads tid < 256 of a CTA finalise channels [c0, c0 + 32); every thread of the CTA must call (two CTA barriers).
+// Threads tid < 256 of a CTA finalise channels [c0, c0 + FIN_CH); every thread of the CTA must call (two CTA barriers).
 // red: >= 2 * FIN_PL * FIN_CH doubles of shared memory.  fp64 partial sums combined in a fixed order (deterministic).
 __device__ __forceinline__ void bn_fin_group(const dp_bn_fin& f, const float* part, int nparts, int c0, int tid, double* red) {
   const int cl = tid % FIN_CH, pl = tid / FIN_CH, c = c0 + cl, Cp = f.Cp;

@@ -179,14 +179,14 @@ wgrad_kernel(Geom g, const T* __restrict__ x, const T* __restrict__ dy, float* _
 
 // dw[k][c][tap] (PyTorch (K,C,kt,kh,kw) order) = sum_split partial[split][k][tap][c], splits added in a fixed
 // order (deterministic).  Threads run along c, so every split's read is a coalesced row.
-constexpr int WR_LANES = 8;    // split-lanes per output element
-constexpr int WR_ELEMS = 32;   // consecutive elements (along c) per CTA
+constexpr int WR_LANES = 16;   // split-lanes per output element (the loop is pure load latency: <= 10 loads per lane at 148 splits)
+constexpr int WR_ELEMS = 16;   // consecutive elements (along c) per CTA
 __global__ void __launch_bounds__(WR_LANES * WR_ELEMS)
 wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                     int nsplit, int K, int C, int Kp, int Cp, int taps) {
   pdl_launch_dependents();
   pdl_wait();
-  // 8 lanes share the <= 295 splits of one element (the loop is pure load latency), each with four independent chains;
+  // 16 lanes share the <= 148 splits of one element (the loop is pure load latency), each with four independent chains;
   // lanes and chains are combined in a fixed order, so the result is deterministic
   __shared__ float red[WR_LANES][WR_ELEMS];
   const int el = threadIdx.x % WR_ELEMS, ln = threadIdx.x / WR_ELEMS;

@@ -49,8 +49,8 @@ for b in blocks:
 def operand_us(name, op):
     cin, cout, taps, sp, rin, rout = geo[name]
     Cp, Kp = c16(cin), c16(cout)
-    if cin == 3:            # packed stem rows: 7 taps of K = 32
-        taps, Cp = 7, 32
+    if cin == 3:            # packed stem row pairs: 4 taps of K = 64
+        taps, Cp = 4, 64
     if op == "fwd":
         nt, N = ntile(Kp)
         cyc = rout / 128 * taps * (Cp / 16) * nt * mma_cycles(N)
