@@ -47,11 +47,12 @@ TRAIN_GFLOP_PER_CLIP = 67.11   # fwd + dgrad + wgrad without the stem's unused d
 
 def measured_traffic(kernel_family: str):
     """Mean DRAM bytes per launch of a kernel family over ALL its launches of one training step, from the committed
-    ncu pass (profiles/*_dram_per_launch.json, written by scripts/summarize_dram.py from
+    ncu pass (profiles/**/*_dram_per_launch.json, written by scripts/summarize_dram.py from
     `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum`): the same set of launches the
     algorithmic bytes per launch are averaged over.  (None, None) if no capture is present."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_dram_per_launch.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "**", "*_dram_per_launch.json"), recursive=True),
+                   key=os.path.basename)
     if not files:
         return None, None
     try:

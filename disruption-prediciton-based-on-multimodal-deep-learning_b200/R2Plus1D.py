@@ -62,6 +62,9 @@ def _call(child: nn.Module, x: torch.Tensor) -> torch.Tensor:
     return child(x)
 
 
+
+_COUNTED = [False]   # True while an enclosing R2Plus1DNet.forward has already counted this batch for every BatchNorm3d
+
 class Conv3dBlock(nn.Module):
     """Conv3d -> BatchNorm3d -> LeakyReLU(alpha)   (reference R2Plus1D.py:25-58)."""
 
@@ -111,7 +114,7 @@ class Conv3dBlock(nn.Module):
         self._refresh_cfg()
         xp = Fn.stem_pack_input(x, geom, mean_bgr)
         z = Fn.stem_conv_bn_act(xp, self.conv.weight, self.bn.weight, self.bn.bias, self, geom)
-        if self.training and self.bn.track_running_stats:
+        if self.training and self.bn.track_running_stats and not _COUNTED[0]:
             self.bn.num_batches_tracked.add_(1)
         return Fn.tag(z, self._cfg.K)
 
@@ -119,7 +122,7 @@ class Conv3dBlock(nn.Module):
         x, was_internal = _enter(x)
         self._refresh_cfg()
         z = Fn.conv_bn_act(x, self.conv.weight, self.bn.weight, self.bn.bias, self)
-        if self.training and self.bn.track_running_stats:
+        if self.training and self.bn.track_running_stats and not _COUNTED[0]:
             self.bn.num_batches_tracked.add_(1)
         Fn.tag(z, self._cfg.K)
         return _leave(z, was_internal)
@@ -201,7 +204,7 @@ class SpatioTemporalResBlock(nn.Module):
                 m._refresh_cfg()
                 params += [m.conv.weight, m.bn.weight, m.bn.bias]
             out = Fn.res_block(x, self, *params)
-            if self.training:
+            if self.training and not _COUNTED[0]:
                 for m in layers:
                     if m.bn.track_running_stats:
                         m.bn.num_batches_tracked.add_(1)
@@ -251,6 +254,21 @@ class R2Plus1DNet(nn.Module):
         """x: (B,3,T,H,W) fp32 clips as the reference's DataLoader yields them, or -- an extension for the
         sliding-window loop -- (B,T,H,W,3) uint8 BGR frames with `mean_bgr` (dataset.py:104-110)."""
         batch_size = x.size(0)
+        # nn.BatchNorm3d counts its training batches (num_batches_tracked, part of the reference's state dict): one
+        # multi-tensor increment for all layers instead of a 4-us kernel between every conv and the next (32 per step)
+        counted = self.training and not _COUNTED[0]
+        if counted:
+            bns = [m for m in self.modules() if isinstance(m, nn.BatchNorm3d) and m.track_running_stats]
+            if bns:
+                torch._foreach_add_([m.num_batches_tracked for m in bns], 1)
+            _COUNTED[0] = True
+        try:
+            return self._forward(x, mean_bgr, batch_size)
+        finally:
+            if counted:
+                _COUNTED[0] = False
+
+    def _forward(self, x: torch.Tensor, mean_bgr, batch_size: int):
         stem = self.conv1.spatio_conv
         geom = None if (_hooked(self.conv1) or _hooked(stem) or _hooked(self.conv1.temporal_conv)) else stem._stem_geom(x)
         if geom is not None:

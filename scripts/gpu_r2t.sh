@@ -3,6 +3,7 @@
 # the per-launch dump of one step and the per-layer roofline table
 mkdir -p gpurun_out
 T=r2t
+timeout 1500 python -m pytest tests -m gpu -x -q --timeout 600 2>&1 | tail -3
 DP_BENCH_DUMP=gpurun_out/${T}_step_dump.txt timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench_train.json 2> gpurun_out/${T}_bench_train.err; echo "train rc=$?" > gpurun_out/${T}_rc.txt
 timeout 300 python bench.py --caller stock --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_bench_train_stock_caller.json 2> gpurun_out/${T}_stock.err; echo "stock rc=$?" >> gpurun_out/${T}_rc.txt
 timeout 300 python bench.py --caller eager --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_bench_train_eager.json 2> gpurun_out/${T}_eager.err; echo "eager rc=$?" >> gpurun_out/${T}_rc.txt
