@@ -311,14 +311,29 @@ add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, 
   }
 }
 
-static int ew_grid(int64_t nvec, int vpr) {
+// grid of a grid-stride elementwise pass: `per_sm` CTAs of 256 threads per SM = exactly the CTAs that are resident at once
+// (one wave: a grid of 8 per SM over a kernel that fits 6 ran a second wave at a third of the occupancy)
+static int ew_grid(int64_t nvec, int vpr, int per_sm = 8) {
   int64_t g = (nvec + 255) / 256;
-  const int64_t cap = (int64_t)num_sms() * 8;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
   if (g > cap) g = cap;
   const int64_t gmin = (vpr + 255) / 256;   // the loop stride must hold at least one full row of vectors
   if (g < gmin) g = gmin;
   if (g < 1) g = 1;
   return (int)g;
+}
+
+// resident CTAs per SM of a 256-thread kernel without dynamic shared memory (cached per kernel and device)
+template <typename K>
+static int resident_ctas(K kernel) {
+  static int cached[DP_MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, 0) != cudaSuccess || n < 1) n = 4;
+    cached[dev] = n;
+  }
+  return cached[dev];
 }
 
 }  // namespace dp
@@ -359,12 +374,11 @@ DP_API int dp_bn_act_apply(const void* y, const float* scale, const float* shift
   DP_REQUIRE(y && scale && shift && z, DP_ERR_SHAPE, "dp_bn_act_apply: NULL pointer");
   DP_REQUIRE(Cp % 8 == 0 && Cp > 0 && Cp <= 1024 && rows > 0, DP_ERR_ALIGN, "dp_bn_act_apply: bad Cp=%d / rows", Cp);
   const int64_t nvec = rows * (Cp / 8);
-  const int grid = ew_grid(nvec, Cp / 8);
   const size_t sm = 0;
   cudaStream_t st_ = as_stream(stream);
 #define DP_APPLY_LAUNCH(T, RES, V)                                                                                    \
-  launch_pdl(bn_act_apply_kernel<T, RES, V>, dim3(grid), dim3(256), sm, st_, (const T*)y, scale, shift, slope,        \
-             (const T*)residual, slope_res, (T*)z, nvec, Cp)
+  launch_pdl(bn_act_apply_kernel<T, RES, V>, dim3(ew_grid(nvec, Cp / 8, resident_ctas(bn_act_apply_kernel<T, RES, V>))), \
+             dim3(256), sm, st_, (const T*)y, scale, shift, slope, (const T*)residual, slope_res, (T*)z, nvec, Cp)
   if (dtype == DP_BF16) {
     if (residual != nullptr) DP_APPLY_LAUNCH(__nv_bfloat16, true, 2); else DP_APPLY_LAUNCH(__nv_bfloat16, false, 4);
   } else {
@@ -444,12 +458,13 @@ DP_API int dp_bn_act_bwd_apply(const void* dz, const void* y, const void* out, c
   DP_REQUIRE(Cp % 8 == 0 && Cp > 0 && Cp <= 1024 && rows > 0, DP_ERR_ALIGN, "dp_bn_act_bwd_apply: bad Cp=%d", Cp);
   DP_REQUIRE(dres == nullptr || out != nullptr, DP_ERR_SHAPE, "dp_bn_act_bwd_apply: dres needs out");
   const int64_t nvec = rows * (Cp / 8);
-  const int grid = ew_grid(nvec, Cp / 8);
   const size_t sm = 0;
   cudaStream_t st_ = as_stream(stream);
 #define DP_BWD_APPLY_LAUNCH(T, OUT, V)                                                                                \
-  launch_pdl(bn_act_bwd_apply_kernel<T, OUT, V>, dim3(grid), dim3(256), sm, st_, (const T*)dz, (const T*)y,           \
-             (const T*)out, scale, shift, mean, rstd, coef, slope, slope_res, (T*)dy, (T*)dres, nvec, Cp)
+  launch_pdl(bn_act_bwd_apply_kernel<T, OUT, V>,                                                                      \
+             dim3(ew_grid(nvec, Cp / 8, resident_ctas(bn_act_bwd_apply_kernel<T, OUT, V>))), dim3(256), sm, st_,      \
+             (const T*)dz, (const T*)y, (const T*)out, scale, shift, mean, rstd, coef, slope, slope_res, (T*)dy,      \
+             (T*)dres, nvec, Cp)
   if (dtype == DP_BF16) {
     if (out != nullptr) DP_BWD_APPLY_LAUNCH(__nv_bfloat16, true, 1); else DP_BWD_APPLY_LAUNCH(__nv_bfloat16, false, 2);
   } else {

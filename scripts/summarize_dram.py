@@ -33,7 +33,7 @@ def family(name):
 
 fam = collections.defaultdict(lambda: {"launches": 0, "us": 0.0, "dram": 0.0})
 with open(os.path.join(out, f"{tag}_step_launches.txt"), "w") as f:
-    f.write("every kernel of ONE eager training step (B = 64, bf16), in launch order: ncu --nvtx --nvtx-include dp_step/ "
+    f.write("every kernel of ONE eager training step (B = 64, bf16), in launch order: ncu --profile-from-start off (bench.py --nvtx-step brackets one step with cudaProfilerStart/Stop) "
             "--metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none\n"
             "(durations under ncu are cold-cache and serialised: compare SHARES, not absolutes)\n\n")
     f.write(f"{'#':>4s} {'us':>9s} {'read MB':>9s} {'write MB':>9s}  kernel\n")
