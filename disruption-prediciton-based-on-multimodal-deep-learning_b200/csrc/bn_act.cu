@@ -13,6 +13,22 @@ namespace dp {
 
 constexpr int RED_THREADS = 256;
 
+// Traversal direction of the passes (option "bn_sweep", bits) -- an experiment kept as an option, OFF by default.
+// Consecutive kernels of a step stream tensors of 0.1-0.9 GB through a 126 MB L2; a consumer that starts where its producer
+// STOPPED could find the producer's last ~50-100 MB still cached.  The conv kernels sweep their tiles front to back, so
+//   bit 0: bn_act_apply runs back to front (reads the end of y the conv just wrote, leaves the START of z for the next conv);
+//   bit 1: the backward reduction sweeps back to front in interleaved row groups (the data gradient that wrote dz stopped
+//          at its end) instead of one contiguous row range per CTA;
+//   bit 2: bn_act_bwd_apply runs front to back right after a stand-alone reduction over the same dz (which stopped at the
+//          front), back to front otherwise (dz comes straight from a data gradient whose epilogue produced the sums).
+// Measured on the whole step (profiles/r2/r2z_option_ab.txt, in-process A/B): 16.67-16.74 ms with 0, 16.76-16.84 ms with 7,
+// 16.67 with 1 -- nothing carries over in L2 between these kernels that the passes could use; streaming (ld.global.cs)
+// loads of the dead operands ("bn_cs") and evict-first activation loads in the conv kernels ("tc_l2hint") change nothing
+// either (16.8-17.0 ms).
+int g_bn_sweep = 0;
+int g_bn_cs = 0;   // option "bn_cs": bit 0 / bit 1: apply / backward-apply read their dead inputs with ld.global.cs
+static const void* g_last_reduce_dz = nullptr;   // dz of the most recent stand-alone backward reduction (bit 2)
+
 // 8 consecutive elements exactly as they sit in memory (4 registers for bf16): the reductions below issue the loads of
 // several rows BEFORE converting any of them, so that many rows are in flight per thread; a load that returns eight
 // converted floats (ld8) makes the compiler serialise rows for lack of registers (measured: 2-4 rows in flight, 81-85 %
@@ -23,6 +39,18 @@ template <> struct Raw8<float> { float4 a, b; };
 __device__ __forceinline__ Raw8<__nv_bfloat16> ld_raw8(const __nv_bfloat16* p) { Raw8<__nv_bfloat16> r; r.u = *reinterpret_cast<const uint4*>(p); return r; }
 __device__ __forceinline__ Raw8<float> ld_raw8(const float* p) {
   Raw8<float> r; r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); return r;
+}
+// CS: evict-first ("streaming") loads for operands nobody reads again soon, so that what the pass WRITES outlives them in L2
+template <bool CS> __device__ __forceinline__ Raw8<__nv_bfloat16> ld_raw8s(const __nv_bfloat16* p) {
+  Raw8<__nv_bfloat16> r;
+  r.u = CS ? __ldcs(reinterpret_cast<const uint4*>(p)) : *reinterpret_cast<const uint4*>(p);
+  return r;
+}
+template <bool CS> __device__ __forceinline__ Raw8<float> ld_raw8s(const float* p) {
+  Raw8<float> r;
+  if (CS) { r.a = __ldcs(reinterpret_cast<const float4*>(p)); r.b = __ldcs(reinterpret_cast<const float4*>(p + 4)); }
+  else { r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); }
+  return r;
 }
 __device__ __forceinline__ f8 cvt8(const Raw8<__nv_bfloat16>& x) {
   f8 r;
@@ -41,7 +69,7 @@ __device__ __forceinline__ f8 cvt8(const Raw8<float>& x) {
 // F: Raw load(int64_t elem_offset) fetches one 8-channel vector of every input stream; acc(raw, a8, b8) accumulates it
 template <typename F>
 __global__ void __launch_bounds__(RED_THREADS, 2)
-col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part, const dp_bn_fin fin) {  // f by value: per-thread register copy
+col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part, const dp_bn_fin fin, int sweep) {  // f by value: per-thread register copy
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[2][RED_THREADS * 8];
@@ -49,26 +77,38 @@ col_reduce2_kernel(F f, int64_t rows, int Cp, float* __restrict__ part, const dp
   const int rpi = RED_THREADS / vpr;             // rows per iteration
   const int active = rpi * vpr;
   const int tid = threadIdx.x;
-  const int64_t rows_per_cta = (rows + gridDim.x - 1) / gridDim.x;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
-  int64_t r1 = r0 + rows_per_cta;
-  if (r1 > rows) r1 = rows;
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; }
   if (tid < active) {
     const int cv = tid % vpr, rl = tid / vpr;
     f.init(cv * 8);                       // this thread's 8 channels never change: parameters live in registers
-    int64_t r = r0 + rl;
     constexpr int U = F::kRowsInFlight;       // rows in flight per thread (two CTAs of 256 threads per SM)
-    for (; r + (U - 1) * rpi < r1; r += U * rpi) {
-      typename F::Raw raw[U];
+    auto range = [&](int64_t r0, int64_t r1) {
+      int64_t r = r0 + rl;
+      for (; r + (U - 1) * rpi < r1; r += U * rpi) {
+        typename F::Raw raw[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) raw[u] = f.load((r + u * rpi) * Cp + cv * 8);
+        for (int u = 0; u < U; ++u) raw[u] = f.load((r + u * rpi) * Cp + cv * 8);
 #pragma unroll
-      for (int u = 0; u < U; ++u) f.acc(raw[u], a, b);   // same order as row-by-row: the sums do not change
+        for (int u = 0; u < U; ++u) f.acc(raw[u], a, b);   // same order as row-by-row: the sums do not change
+      }
+      for (; r < r1; r += rpi) f.acc(f.load(r * Cp + cv * 8), a, b);
+    };
+    if (sweep == 0) {   // one contiguous row range per CTA
+      const int64_t rows_per_cta = (rows + gridDim.x - 1) / gridDim.x;
+      const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+      const int64_t r1 = r0 + rows_per_cta;
+      range(r0, r1 > rows ? rows : r1);
+    } else {            // row groups interleaved over the CTAs: the grid sweeps the tensor front to back (1) or back to front (2)
+      const int64_t rg = (int64_t)U * rpi;
+      const int64_t ngroups = (rows + rg - 1) / rg;
+      for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t gg = sweep == 2 ? ngroups - 1 - g : g;
+        const int64_t r1 = (gg + 1) * rg;
+        range(gg * rg, r1 > rows ? rows : r1);
+      }
     }
-    for (; r < r1; r += rpi) f.acc(f.load(r * Cp + cv * 8), a, b);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[0][tid * 8 + j] = a[j]; red[1][tid * 8 + j] = b[j]; }
@@ -155,12 +195,13 @@ int bn_stats_launch(const void* y, int64_t rows, int Cp, int dtype, float* part,
   DP_REQUIRE(rows > 0, DP_ERR_SHAPE, "bn_stats: no rows");
   const int grid = reduce_grid(rows);
   const dp_bn_fin f_ = fin ? *fin : kNoFin;
+  const int sweep = 0;   // (stand-alone forward statistics: fp32 validation mode and tiles the conv epilogues do not cover)
   if (dtype == DP_BF16) {
     StatsF<__nv_bfloat16> f{(const __nv_bfloat16*)y};
-    launch_pdl(col_reduce2_kernel<StatsF<__nv_bfloat16>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+    launch_pdl(col_reduce2_kernel<StatsF<__nv_bfloat16>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_, sweep);
   } else {
     StatsF<float> f{(const float*)y};
-    launch_pdl(col_reduce2_kernel<StatsF<float>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+    launch_pdl(col_reduce2_kernel<StatsF<float>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_, sweep);
   }
   if (nparts != nullptr) *nparts = grid;
   return check_launch("bn_stats");
@@ -193,7 +234,7 @@ __global__ void bn_eval_coeffs_kernel(const float* rm, const float* rv, const fl
 // Grid-stride loops whose stride is a multiple of the vectors-per-row, so a thread always works on the same
 // 8 channels and keeps their parameters in registers (no per-element parameter traffic).
 // V vectors in flight per thread: the raw 16-byte loads of all V are issued before any is converted (see Raw8)
-template <typename T, bool HAS_RES, int V>
+template <typename T, bool HAS_RES, int V, bool CS, bool REV>
 __global__ void __launch_bounds__(256)
 bn_act_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                     float slope, const T* __restrict__ residual, float slope_res, T* __restrict__ z,
@@ -205,7 +246,10 @@ bn_act_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, co
   const int64_t stride = (total / vpr) * vpr;
   const int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v0 >= stride) return;
-  const int c0 = (int)(v0 % vpr) * 8;
+  // REV: the grid sweeps the tensor back to front; nvec and the stride are multiples of vpr, so at(v) stays in one column
+  const int64_t last = nvec - 1;
+#define at(v) (REV ? last - (v) : (v))
+  const int c0 = (int)(at(v0) % vpr) * 8;
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
@@ -225,20 +269,21 @@ bn_act_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, co
     Raw8<T> ya[V], ra[V];
 #pragma unroll
     for (int u = 0; u < V; ++u) {
-      ya[u] = ld_raw8(y + (v + u * stride) * 8);
-      if (HAS_RES) ra[u] = ld_raw8(residual + (v + u * stride) * 8);
+      ya[u] = ld_raw8s<CS>(y + at(v + u * stride) * 8);
+      if (HAS_RES) ra[u] = ld_raw8s<CS>(residual + at(v + u * stride) * 8);
     }
 #pragma unroll
-    for (int u = 0; u < V; ++u) one(ya[u], ra[u], v + u * stride);
+    for (int u = 0; u < V; ++u) one(ya[u], ra[u], at(v + u * stride));
   }
   for (; v < nvec; v += stride) {
-    Raw8<T> ya = ld_raw8(y + v * 8), ra;
-    if (HAS_RES) ra = ld_raw8(residual + v * 8);
-    one(ya, ra, v);
+    Raw8<T> ya = ld_raw8s<CS>(y + at(v) * 8), ra;
+    if (HAS_RES) ra = ld_raw8s<CS>(residual + at(v) * 8);
+    one(ya, ra, at(v));
   }
+#undef at
 }
 
-template <typename T, bool HAS_OUT, int V>
+template <typename T, bool HAS_OUT, int V, bool CS, bool REV>
 __global__ void __launch_bounds__(256, 4)   // 64 registers: four CTAs per SM
 bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y, const T* __restrict__ out,
                         const float* __restrict__ scale, const float* __restrict__ shift,
@@ -252,7 +297,9 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y, const
   const int64_t stride = (total / vpr) * vpr;
   const int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v0 >= stride) return;
-  const int c0 = (int)(v0 % vpr) * 8;
+  const int64_t last = nvec - 1;
+#define at(v) (REV ? last - (v) : (v))   // (see bn_act_apply_kernel)
+  const int c0 = (int)(at(v0) % vpr) * 8;
   // dy = scale*(g - c0 - xhat*c1),  xhat = (y - mean)*rstd   =>   dy = scale*g + ka + kb*y
   float sc[8], sh[8], ka[8], kb[8];
 #pragma unroll
@@ -284,18 +331,19 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ y, const
     Raw8<T> gr[V], yr[V], orr[V];
 #pragma unroll
     for (int u = 0; u < V; ++u) {
-      gr[u] = ld_raw8(dz + (v + u * stride) * 8);
-      yr[u] = ld_raw8(y + (v + u * stride) * 8);
-      if (HAS_OUT) orr[u] = ld_raw8(out + (v + u * stride) * 8);
+      gr[u] = ld_raw8s<CS>(dz + at(v + u * stride) * 8);
+      yr[u] = ld_raw8s<CS>(y + at(v + u * stride) * 8);
+      if (HAS_OUT) orr[u] = ld_raw8s<CS>(out + at(v + u * stride) * 8);
     }
 #pragma unroll
-    for (int u = 0; u < V; ++u) one(gr[u], yr[u], orr[u], v + u * stride);
+    for (int u = 0; u < V; ++u) one(gr[u], yr[u], orr[u], at(v + u * stride));
   }
   for (; v < nvec; v += stride) {
-    Raw8<T> gr = ld_raw8(dz + v * 8), yr = ld_raw8(y + v * 8), orr;
-    if (HAS_OUT) orr = ld_raw8(out + v * 8);
-    one(gr, yr, orr, v);
+    Raw8<T> gr = ld_raw8s<CS>(dz + at(v) * 8), yr = ld_raw8s<CS>(y + at(v) * 8), orr;
+    if (HAS_OUT) orr = ld_raw8s<CS>(out + at(v) * 8);
+    one(gr, yr, orr, at(v));
   }
+#undef at
 }
 
 template <typename T>
@@ -356,7 +404,7 @@ DP_API int dp_bn_finalize(const float* part, int nparts, int C, int Cp, double c
   dp_bn_fin f = {};
   f.kind = 1; f.C = C; f.Cp = Cp; f.count = count; f.gamma = gamma; f.beta = beta; f.eps = eps; f.momentum = momentum;
   f.running_mean = running_mean; f.running_var = running_var; f.mean = mean; f.rstd = rstd; f.scale = scale; f.shift = shift;
-  launch_pdl(bn_finalize_group_kernel, dim3(ceil_div(Cp, FIN_CH)), dim3(FIN_CH * FIN_PL), 0, as_stream(stream), part, nparts, f);
+  launch_pdl_small(bn_finalize_group_kernel, dim3(ceil_div(Cp, FIN_CH)), dim3(FIN_CH * FIN_PL), 0, as_stream(stream), part, nparts, f);
   return check_launch("dp_bn_finalize");
 }
 
@@ -376,14 +424,21 @@ DP_API int dp_bn_act_apply(const void* y, const float* scale, const float* shift
   const int64_t nvec = rows * (Cp / 8);
   const size_t sm = 0;
   cudaStream_t st_ = as_stream(stream);
-#define DP_APPLY_LAUNCH(T, RES, V)                                                                                    \
-  launch_pdl(bn_act_apply_kernel<T, RES, V>, dim3(ew_grid(nvec, Cp / 8, resident_ctas(bn_act_apply_kernel<T, RES, V>))), \
-             dim3(256), sm, st_, (const T*)y, scale, shift, slope, (const T*)residual, slope_res, (T*)z, nvec, Cp)
+#define DP_APPLY_LAUNCH_(T, RES, V, CS, REV)                                                                         \
+  launch_pdl(bn_act_apply_kernel<T, RES, V, CS, REV>,                                                                 \
+             dim3(ew_grid(nvec, Cp / 8, resident_ctas(bn_act_apply_kernel<T, RES, V, CS, REV>))), dim3(256), sm, st_, \
+             (const T*)y, scale, shift, slope, (const T*)residual, slope_res, (T*)z, nvec, Cp)
+#define DP_APPLY_LAUNCH(T, RES, V) do {                                                                               \
+    if (cs) { if (rev) DP_APPLY_LAUNCH_(T, RES, V, true, true); else DP_APPLY_LAUNCH_(T, RES, V, true, false); }      \
+    else { if (rev) DP_APPLY_LAUNCH_(T, RES, V, false, true); else DP_APPLY_LAUNCH_(T, RES, V, false, false); } } while (0)
+  const int rev = g_bn_sweep & 1;
+  const bool cs = (g_bn_cs & 1) != 0;
   if (dtype == DP_BF16) {
     if (residual != nullptr) DP_APPLY_LAUNCH(__nv_bfloat16, true, 2); else DP_APPLY_LAUNCH(__nv_bfloat16, false, 4);
   } else {
     if (residual != nullptr) DP_APPLY_LAUNCH(float, true, 1); else DP_APPLY_LAUNCH(float, false, 2);
   }
+#undef DP_APPLY_LAUNCH_
 #undef DP_APPLY_LAUNCH
   return check_launch("dp_bn_act_apply");
 }
@@ -396,23 +451,25 @@ static int bwd_reduce_launch(const void* dz, const void* y, const void* out, con
   const int grid = reduce_grid(rows);
   cudaStream_t s = as_stream(stream);
   const dp_bn_fin f_ = fin ? *fin : kNoFin;
+  const int sweep = (g_bn_sweep & 2) ? 2 : 0;
+  g_last_reduce_dz = dz;
   if (dtype == DP_BF16) {
     if (out != nullptr) {
       BwdReduceF<__nv_bfloat16, true> f{(const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, (const __nv_bfloat16*)out,
                                         scale, shift, mean, rstd, slope, slope_res};
-      launch_pdl(col_reduce2_kernel<BwdReduceF<__nv_bfloat16, true>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+      launch_pdl(col_reduce2_kernel<BwdReduceF<__nv_bfloat16, true>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_, sweep);
     } else {
       BwdReduceF<__nv_bfloat16, false> f{(const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, nullptr,
                                          scale, shift, mean, rstd, slope, slope_res};
-      launch_pdl(col_reduce2_kernel<BwdReduceF<__nv_bfloat16, false>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+      launch_pdl(col_reduce2_kernel<BwdReduceF<__nv_bfloat16, false>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_, sweep);
     }
   } else {
     if (out != nullptr) {
       BwdReduceF<float, true> f{(const float*)dz, (const float*)y, (const float*)out, scale, shift, mean, rstd, slope, slope_res};
-      launch_pdl(col_reduce2_kernel<BwdReduceF<float, true>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+      launch_pdl(col_reduce2_kernel<BwdReduceF<float, true>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_, sweep);
     } else {
       BwdReduceF<float, false> f{(const float*)dz, (const float*)y, nullptr, scale, shift, mean, rstd, slope, slope_res};
-      launch_pdl(col_reduce2_kernel<BwdReduceF<float, false>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_);
+      launch_pdl(col_reduce2_kernel<BwdReduceF<float, false>>, dim3(grid), dim3(RED_THREADS), 0, s, f, rows, Cp, part, f_, sweep);
     }
   }
   if (nparts != nullptr) *nparts = grid;
@@ -445,7 +502,7 @@ DP_API int dp_bn_bwd_finalize(const float* part, int nparts, int C, int Cp, doub
   dp_bn_fin f = {};
   f.kind = 2; f.C = C; f.Cp = Cp; f.count = count; f.mean = const_cast<float*>(mean); f.rstd = const_cast<float*>(rstd);
   f.dgamma = dgamma; f.dbeta = dbeta; f.coef = coef;
-  launch_pdl(bn_finalize_group_kernel, dim3(ceil_div(Cp, FIN_CH)), dim3(FIN_CH * FIN_PL), 0, as_stream(stream), part, nparts, f);
+  launch_pdl_small(bn_finalize_group_kernel, dim3(ceil_div(Cp, FIN_CH)), dim3(FIN_CH * FIN_PL), 0, as_stream(stream), part, nparts, f);
   return check_launch("dp_bn_bwd_finalize");
 }
 
@@ -460,16 +517,26 @@ DP_API int dp_bn_act_bwd_apply(const void* dz, const void* y, const void* out, c
   const int64_t nvec = rows * (Cp / 8);
   const size_t sm = 0;
   cudaStream_t st_ = as_stream(stream);
-#define DP_BWD_APPLY_LAUNCH(T, OUT, V)                                                                                \
-  launch_pdl(bn_act_bwd_apply_kernel<T, OUT, V>,                                                                      \
-             dim3(ew_grid(nvec, Cp / 8, resident_ctas(bn_act_bwd_apply_kernel<T, OUT, V>))), dim3(256), sm, st_,      \
-             (const T*)dz, (const T*)y, (const T*)out, scale, shift, mean, rstd, coef, slope, slope_res, (T*)dy,      \
+#define DP_BWD_APPLY_LAUNCH_(T, OUT, V, CS, REV)                                                                     \
+  launch_pdl(bn_act_bwd_apply_kernel<T, OUT, V, CS, REV>,                                                             \
+             dim3(ew_grid(nvec, Cp / 8, resident_ctas(bn_act_bwd_apply_kernel<T, OUT, V, CS, REV>))), dim3(256), sm,  \
+             st_, (const T*)dz, (const T*)y, (const T*)out, scale, shift, mean, rstd, coef, slope, slope_res, (T*)dy, \
              (T*)dres, nvec, Cp)
+#define DP_BWD_APPLY_LAUNCH(T, OUT, V) do {                                                                           \
+    if (cs) { if (rev) DP_BWD_APPLY_LAUNCH_(T, OUT, V, true, true); else DP_BWD_APPLY_LAUNCH_(T, OUT, V, true, false); } \
+    else { if (rev) DP_BWD_APPLY_LAUNCH_(T, OUT, V, false, true); else DP_BWD_APPLY_LAUNCH_(T, OUT, V, false, false); } } while (0)
+  // after a stand-alone back-to-front reduction over this dz the cache holds the FRONT of dz and y; a dz that comes straight
+  // from a data gradient (sums in its epilogue) is cached at its END
+  const bool after_reduce = (g_bn_sweep & 2) && g_last_reduce_dz == dz;
+  const int rev = (g_bn_sweep & 4) ? (after_reduce ? 0 : 1) : 0;
+  g_last_reduce_dz = nullptr;
+  const bool cs = (g_bn_cs & 2) != 0;
   if (dtype == DP_BF16) {
     if (out != nullptr) DP_BWD_APPLY_LAUNCH(__nv_bfloat16, true, 1); else DP_BWD_APPLY_LAUNCH(__nv_bfloat16, false, 2);
   } else {
     if (out != nullptr) DP_BWD_APPLY_LAUNCH(float, true, 1); else DP_BWD_APPLY_LAUNCH(float, false, 1);
   }
+#undef DP_BWD_APPLY_LAUNCH_
 #undef DP_BWD_APPLY_LAUNCH
   return check_launch("dp_bn_act_bwd_apply");
 }

@@ -15,6 +15,8 @@ size_t simt_wgrad_workspace(const dp_conv_desc* d);
 int wgrad_reduce_launch(const float* partial, float* dw, int nsplit, int K, int C, int Kp, int Cp, int taps,
                         cudaStream_t s);
 extern int g_strict_tc;   // conv_api.cu: DP_IMPL_AUTO refuses the CUDA-core fallback on bf16 tensors
+extern int g_bn_sweep;    // bn_act.cu: traversal direction of the BatchNorm passes (bits, see there)
+extern int g_bn_cs;       // bn_act.cu: streaming loads of dead operands in the elementwise BatchNorm passes
 int wg_option(const char* name, int value, bool set);
 int tc_option(const char* name, int value, bool set);
 

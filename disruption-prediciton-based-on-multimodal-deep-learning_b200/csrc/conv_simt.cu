@@ -223,7 +223,7 @@ wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
 int wgrad_reduce_launch(const float* partial, float* dw, int nsplit, int K, int C, int Kp, int Cp, int taps,
                         cudaStream_t s) {
   const int total = K * taps * Cp;
-  launch_pdl(wgrad_reduce_kernel, dim3(ceil_div(total, WR_ELEMS)), dim3(WR_LANES * WR_ELEMS), 0, s, partial, dw, nsplit, K, C, Kp,
+  launch_pdl_small(wgrad_reduce_kernel, dim3(ceil_div(total, WR_ELEMS)), dim3(WR_LANES * WR_ELEMS), 0, s, partial, dw, nsplit, K, C, Kp,
              Cp, taps);
   return check_launch("conv_wgrad_reduce");
 }

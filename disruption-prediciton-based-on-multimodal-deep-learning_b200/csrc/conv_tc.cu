@@ -86,6 +86,7 @@ struct TcParams {
   long long a_off_k[8];
   short dWk[8], dHk[8], dTk[8];
   int dbg_skip;  // development: 1 = no epilogue data movement / stores, 2 = no TMA loads, 4 = one MMA per load
+  int l2_hint;   // 1: activation boxes are loaded with an L2 evict-first policy (what the kernel WRITES outlives them in L2)
   long long a_off, a_sw, a_sh, a_st, a_sb;  // addend view: element offset / strides of (w,h,t,b) in the dst tensor
   signed char off_w[TC_MAX_LOADS], off_h[TC_MAX_LOADS], off_t[TC_MAX_LOADS];
   short tap0[TC_MAX_LOADS];
@@ -228,6 +229,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t stage_bytes = (uint32_t)p.stage_bytes, slot_f = (uint32_t)p.slot_bytes;
     const uint32_t slot_t = (uint32_t)(p.unit_mode ? p.slot_bytes_t : p.slot_bytes), b_sub_bytes = (uint32_t)p.b_sub_bytes;
     const int sw = p.bw * p.mw, sh = p.bh * p.mh, st_ = p.bt * p.mt;
+    const bool l2_hint = p.l2_hint != 0;
+    const uint64_t pol_first = l2_policy_evict_first();
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti.next(), ++it) {
@@ -250,7 +253,10 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           uint32_t bytes = 0;
           for (int j = 0; j < cnt; ++j) {
             const bool tail = cb == tailcb;
-            tma_load_5d(tail ? &tmA2 : &tmA, full_bar(sidx), sa, cb * CB, w0 + p.off_w[l], h0 + p.off_h[l], t0 + p.off_t[l], b);
+            if (l2_hint)
+              tma_load_5d_hint(tail ? &tmA2 : &tmA, full_bar(sidx), sa, cb * CB, w0 + p.off_w[l], h0 + p.off_h[l], t0 + p.off_t[l], b, pol_first);
+            else
+              tma_load_5d(tail ? &tmA2 : &tmA, full_bar(sidx), sa, cb * CB, w0 + p.off_w[l], h0 + p.off_h[l], t0 + p.off_t[l], b);
             const uint32_t sz = tail ? slot_t : slot_f;
             bytes += tail ? tx_t : tx;
             if (!resident) {
@@ -893,7 +899,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64, g_opt_mt = 0, g_opt_classes = 1, g_opt_pub_sub_min = 64, g_opt_fine_n = 48;
+static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64, g_opt_mt = 0, g_opt_classes = 1, g_opt_pub_sub_min = 64, g_opt_fine_n = 48, g_opt_l2hint = 0;
 int tc_option(const char* name, int value, bool set) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_opt_halo;
@@ -905,6 +911,7 @@ int tc_option(const char* name, int value, bool set) {
   else if (!strcmp(name, "tc_chunked")) slot = &g_opt_chunked;
   else if (!strcmp(name, "tc_st_bufs")) slot = &g_opt_st_bufs;
   else if (!strcmp(name, "tc_dbg_skip")) slot = &g_opt_dbg_skip;
+  else if (!strcmp(name, "tc_l2hint")) slot = &g_opt_l2hint;   // evict-first loads of the activation operand
   else if (!strcmp(name, "tc_lps_max")) slot = &g_opt_lps_max;
   else if (!strcmp(name, "tc_reg_stats")) slot = &g_opt_reg_stats;
   else if (!strcmp(name, "tc_dual_mma")) slot = &g_opt_dual;
@@ -1352,6 +1359,7 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   DP_REQUIRE(!epi_bn || (part == nullptr && !bwd_stats && bn_ss != nullptr), DP_ERR_SHAPE,
              "tcgen05 conv: the fused BatchNorm epilogue excludes statistics");
   p.dbg_skip = g_opt_dbg_skip;
+  p.l2_hint = g_opt_l2hint;
   const CUtensorMapSwizzle sw = p.CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                            : (p.CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap tmA, tmB, tmD;
@@ -1690,6 +1698,9 @@ int tc_describe_plan(const dp_conv_desc* d, int op, int has_stats, char* out, si
 DP_API int dp_set_option(const char* name, int value) {
   if (name == nullptr) return DP_ERR_SHAPE;
   if (!strcmp(name, "pdl")) { dp::g_pdl = value ? 1 : 0; return DP_OK; }
+  if (!strcmp(name, "pdl_small")) { dp::g_pdl_small = value ? 1 : 0; return DP_OK; }
+  if (!strcmp(name, "bn_sweep")) { dp::g_bn_sweep = value; return DP_OK; }
+  if (!strcmp(name, "bn_cs")) { dp::g_bn_cs = value; return DP_OK; }
   if (!strcmp(name, "strict_tc")) { dp::g_strict_tc = value ? 1 : 0; return DP_OK; }
   if (dp::tc_option(name, value, true) >= 0 || dp::wg_option(name, value, true) >= 0) return DP_OK;
   dp::set_error("dp_set_option: unknown option '%s'", name);
@@ -1702,6 +1713,9 @@ DP_API int dp_conv_describe_plan(const dp_conv_desc* d, int op, int has_stats, c
 DP_API int dp_get_option(const char* name) {
   if (name == nullptr) return -1;
   if (!strcmp(name, "pdl")) return dp::g_pdl;
+  if (!strcmp(name, "pdl_small")) return dp::g_pdl_small;
+  if (!strcmp(name, "bn_sweep")) return dp::g_bn_sweep;
+  if (!strcmp(name, "bn_cs")) return dp::g_bn_cs;
   if (!strcmp(name, "strict_tc")) return dp::g_strict_tc;
   const int v = dp::tc_option(name, 0, false);
   return v >= 0 ? v : dp::wg_option(name, 0, false);

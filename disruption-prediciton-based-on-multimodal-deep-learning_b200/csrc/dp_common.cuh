@@ -44,16 +44,27 @@ int num_sms();          // of the current device
 // A step is ~370 short kernels; launched with programmatic stream serialization a kernel's CTAs may become resident
 // while the previous kernel drains (its prologue overlaps the predecessor's tail).  Every kernel launched this way
 // executes pdl_wait() before its first global-memory access and pdl_launch_dependents() at its start.
-extern int g_pdl;
+extern int g_pdl;       // every kernel launched through launch_pdl (measured slower on the whole step: off)
+extern int g_pdl_small; // only the small latency-bound kernels that sit between two big ones (launch_pdl_small)
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+inline cudaError_t launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = on ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  return launch_pdl_if(g_pdl != 0, kernel, grid, block, smem, s, static_cast<Args&&>(args)...);
+}
+// a few CTAs of 256 threads that fit beside the producer's CTAs: they become resident while the producer drains and sit
+// in griddepcontrol.wait, so their launch latency leaves the critical path
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_small(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  return launch_pdl_if(g_pdl != 0 || g_pdl_small != 0, kernel, grid, block, smem, s, static_cast<Args&&>(args)...);
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

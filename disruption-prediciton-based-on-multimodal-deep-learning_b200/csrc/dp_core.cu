@@ -6,7 +6,8 @@ namespace dp {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
-int g_pdl = 0;   // measured: no gain on this step (23.0 ms with, 22.5 ms without), kept as an option
+int g_pdl = 0;         // measured: slower on the whole step (18.91 vs 18.24 ms), kept as an option
+int g_pdl_small = 0;   // programmatic dependent launch of the small finalize / split-reduce kernels only
 long long* g_dbg = nullptr;
 size_t g_dbg_slots = 0;
 

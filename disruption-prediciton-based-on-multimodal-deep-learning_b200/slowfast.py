@@ -30,6 +30,9 @@ def _t3(v):
     return tuple(v) if isinstance(v, (tuple, list)) else (v, v, v)
 
 
+
+_COUNTED = [False]   # True while SlowFastEncoder.forward has already counted this batch for every BatchNorm3d
+
 class _ConvBN:
     """Adapter handing one (nn.Conv3d, nn.BatchNorm3d) pair of a reference-shaped module tree to the fused layer
     functions.  Not an nn.Module: the parameters stay registered under their reference names."""
@@ -80,7 +83,7 @@ class _ConvBN:
                 z = Fn.conv_bn_act(x, self.conv.weight, bn.weight, bn.bias, self)
         finally:
             self._bias_fixups(before=False)
-        if self.training and bn.track_running_stats:
+        if self.training and bn.track_running_stats and not _COUNTED[0]:
             bn.num_batches_tracked.add_(1)
         return Fn.tag(z, self._cfg.K)
 
@@ -303,10 +306,22 @@ class SlowFastEncoder(nn.Module):
 
     def forward(self, x: torch.Tensor):
         L.require_device()
-        x_slow, x_fast = self.split_slow_fast(x)
-        x_fast, laterals = self.fastnet(x_fast.contiguous())
-        x_slow = self.slownet((x_slow.contiguous(), laterals))
-        return torch.cat([x_slow, x_fast], dim=1)
+        # one multi-tensor increment of every BatchNorm3d batch counter (the per-layer increments are 4-us launches
+        # between the convs); the layers see _COUNTED and skip theirs
+        counted = self.training and not _COUNTED[0]
+        if counted:
+            bns = [m for m in self.modules() if isinstance(m, nn.BatchNorm3d) and m.track_running_stats]
+            if bns:
+                torch._foreach_add_([m.num_batches_tracked for m in bns], 1)
+            _COUNTED[0] = True
+        try:
+            x_slow, x_fast = self.split_slow_fast(x)
+            x_fast, laterals = self.fastnet(x_fast.contiguous())
+            x_slow = self.slownet((x_slow.contiguous(), laterals))
+            return torch.cat([x_slow, x_fast], dim=1)
+        finally:
+            if counted:
+                _COUNTED[0] = False
 
     def get_output_shape(self):
         """The reference pushes a zero clip through both pathways on the CPU in TRAINING mode (slowfast.py:137-141).
