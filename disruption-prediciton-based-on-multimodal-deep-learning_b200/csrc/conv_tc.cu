@@ -86,6 +86,7 @@ struct TcParams {
   long long a_off_k[8];
   short dWk[8], dHk[8], dTk[8];
   int dbg_skip;  // development: 1 = no epilogue data movement / stores, 2 = no TMA loads, 4 = one MMA per load
+  int pC, n_base;   // statistics partials: row pitch (channels of the full destination) and first channel of this launch
   int l2_hint;   // 1: activation boxes are loaded with an L2 evict-first policy (what the kernel WRITES outlives them in L2)
   long long a_off, a_sw, a_sh, a_st, a_sb;  // addend view: element offset / strides of (w,h,t,b) in the dst tensor
   signed char off_w[TC_MAX_LOADS], off_h[TC_MAX_LOADS], off_t[TC_MAX_LOADS];
@@ -820,25 +821,26 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
       }
       named_bar_sync(1, TC_EPI);
-      float* prow = part + (int64_t)blockIdx.x * 2 * p.dC;
+      float* prow = part + (int64_t)blockIdx.x * 2 * p.pC + p.n_base;
       for (int c = et; c < p.Ntile; c += TC_EPI) {
         float a0 = 0.f, b0 = 0.f;
 #pragma unroll
         for (int g = 0; g < 4; ++g) { a0 += scratch[(g * p.Ntile + c) * 2 + 0]; b0 += scratch[(g * p.Ntile + c) * 2 + 1]; }
         prow[c] = a0;
-        prow[p.dC + c] = b0;
+        prow[p.pC + c] = b0;
       }
     }
     if (legacy_stats) {
       named_bar_sync(1, TC_EPI);
-      for (int i = et; i < 2 * p.dC; i += TC_EPI) part[(int64_t)blockIdx.x * 2 * p.dC + i] = stats_sm[i];
+      for (int i = et; i < 2 * p.dC; i += TC_EPI)
+        part[(int64_t)blockIdx.x * 2 * p.pC + p.n_base + (i < p.dC ? i : p.pC + i - p.dC)] = stats_sm[i];
     }
     if (p.mma_stats && chalf == 0) {
       // all statistics MMAs of this CTA have retired once the last staged tile's are done
       const int last = it - 1;
       mbar_wait(sdone_bar(last % p.st_bufs), (uint32_t)((last / p.st_bufs) & 1));
       tc_fence_after();
-      float* prow = part + (int64_t)blockIdx.x * 2 * p.dC;
+      float* prow = part + (int64_t)blockIdx.x * 2 * p.pC + p.n_base;
       const uint32_t lane_base = (uint32_t)(q * 32) << 16;
       if (q == 0) {   // column sums: every row of D_s is the same, row 0 lives in TMEM lane 0
         for (int n0 = 0; n0 < p.Ntile; n0 += 16) {
@@ -862,7 +864,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int j = 0; j < 16; ++j)
             if (lane == n0 + j) val = __uint_as_float(v[j]);
         }
-        if (lane < per_warp && cbase + lane < p.Ntile) prow[p.dC + cbase + lane] = val;
+        if (lane < per_warp && cbase + lane < p.Ntile) prow[p.pC + cbase + lane] = val;
       }
     }
   }
@@ -899,7 +901,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64, g_opt_mt = 0, g_opt_classes = 1, g_opt_pub_sub_min = 64, g_opt_fine_n = 48, g_opt_l2hint = 0;
+static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64, g_opt_mt = 0, g_opt_classes = 1, g_opt_pub_sub_min = 64, g_opt_fine_n = 48, g_opt_l2hint = 0, g_opt_nsplit = 0;
 int tc_option(const char* name, int value, bool set) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_opt_halo;
@@ -911,6 +913,7 @@ int tc_option(const char* name, int value, bool set) {
   else if (!strcmp(name, "tc_chunked")) slot = &g_opt_chunked;
   else if (!strcmp(name, "tc_st_bufs")) slot = &g_opt_st_bufs;
   else if (!strcmp(name, "tc_dbg_skip")) slot = &g_opt_dbg_skip;
+  else if (!strcmp(name, "tc_nsplit")) slot = &g_opt_nsplit;   // forward: output channels in two launches when that makes the weights resident
   else if (!strcmp(name, "tc_l2hint")) slot = &g_opt_l2hint;   // evict-first loads of the activation operand
   else if (!strcmp(name, "tc_lps_max")) slot = &g_opt_lps_max;
   else if (!strcmp(name, "tc_reg_stats")) slot = &g_opt_reg_stats;
@@ -943,6 +946,9 @@ struct GatherProblem {
   int vo_t, vo_h, vo_w, vs_t, vs_h, vs_w;
   // optional source view: element strides of (w,h,t,b); 0 = dense NDHWC (the packed stem rows overlap in w)
   long long ss_w, ss_h, ss_t, ss_b;
+  // output-channel split (forward): this launch produces channels [n0, n0 + dC) of a destination with dCf channels
+  // (dCf == 0: the destination has dC channels); weights and statistics partials are offset the same way
+  int dCf = 0, n0 = 0;
 };
 
 struct TcPlan {
@@ -1367,6 +1373,9 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   int rc = encode_act_map(&tmA, src, g.sC, g.sW, g.sH, g.sT, g.B, plan.a_box, plan.a_estride, sw, vstr);
   if (rc != DP_OK) return rc;
   const int taps = g.Kt * g.Kh * g.Kw;
+  const int dCf = g.dCf ? g.dCf : g.dC;
+  p.pC = dCf; p.n_base = g.n0;
+  wgt = (const __nv_bfloat16*)wgt + (size_t)g.n0 * taps * g.sC;   // rows [n0, n0 + dC) of w[Kp][taps][Cp]
   rc = encode_wgt_map(&tmB, wgt, taps * g.sC, g.dC, p.CB, p.Ntile, sw);
   if (rc != DP_OK) return rc;
   CUtensorMap tmA2 = tmA, tmB2 = tmB;
@@ -1380,11 +1389,11 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
   }
   // one TMA store moves one 128-row sub-tile
   const int dbox[5] = {p.cw, p.sub_ow ? p.sub_ow : p.bw, p.sub_oh ? p.sub_oh : p.bh, p.sub_ot ? p.sub_ot : p.bt, 1};
-  p.a_sw = (long long)g.vs_w * g.dC;
-  p.a_sh = (long long)g.vs_h * g.FW * g.dC;
-  p.a_st = (long long)g.vs_t * g.FH * g.FW * g.dC;
-  p.a_sb = (long long)g.FT * g.FH * g.FW * g.dC;
-  p.a_off = (((long long)g.vo_t * g.FH + g.vo_h) * g.FW + g.vo_w) * g.dC;
+  p.a_sw = (long long)g.vs_w * dCf;
+  p.a_sh = (long long)g.vs_h * g.FW * dCf;
+  p.a_st = (long long)g.vs_t * g.FH * g.FW * dCf;
+  p.a_sb = (long long)g.FT * g.FH * g.FW * dCf;
+  p.a_off = (((long long)g.vo_t * g.FH + g.vo_h) * g.FW + g.vo_w) * dCf + g.n0;
   CUtensorMap tmDk[4];
   if (cg == nullptr) {
     rc = encode_view_map(&tmD, (const __nv_bfloat16*)dst + p.a_off, g.dC, g.dW, g.dH, g.dT, g.B, p.a_sw, p.a_sh, p.a_st,
@@ -1535,9 +1544,43 @@ bool tc_dgrad_supported(const dp_conv_desc* d) {
   return true;
 }
 
+// Output-channel split of a forward conv whose weights do not fit beside the pipeline (64 -> 144 channels, 9 taps: 166 KB):
+// unsplit, every 128-pixel tile streams all of them from L2 again (935 MB of L2 reads per launch at B = 64, the layer's
+// actual bound); as two launches over channels [0, na) and [na, dC) each half is resident in shared memory for the whole
+// launch, the tiles are narrow enough for register statistics and 256-pixel tiles, and the input is read twice instead.
+static bool fwd_split(const GatherProblem& g, bool has_stats, int* na) {
+  if (!g_opt_nsplit || g.dC <= 96 || g.dC > 256) return false;
+  TcPlan whole, a, b;
+  if (!plan_gather(g, has_stats, &whole) || whole.p.w_resident) return false;
+  if (g_opt_nsplit == 1 && whole.p.num_tiles < 4 * whole.grid) return false;   // too few tiles per CTA to pay for a second launch (2: always, tests)
+  GatherProblem ga = g, gb = g;
+  ga.dC = round_up(g.dC / 2, 16);
+  gb.dC = g.dC - ga.dC;
+  if (gb.dC < 16) return false;
+  if (!plan_gather(ga, has_stats, &a) || !plan_gather(gb, has_stats, &b)) return false;
+  if (!a.p.w_resident || !b.p.w_resident || a.grid != b.grid) return false;
+  *na = ga.dC;
+  return true;
+}
+
 int tc_conv_fwd(const dp_conv_desc* d, const void* x, const void* w, void* y, float* part, int* nparts,
                 cudaStream_t s, const dp_bn_fin* fin) {
-  return launch_gather(fwd_problem(d), x, w, y, nullptr, part, nparts, s, nullptr, nullptr, 1.f, 0, 1.f, nullptr, 0, fin);
+  const GatherProblem g = fwd_problem(d);
+  int na = 0;
+  if (fin == nullptr && fwd_split(g, part != nullptr, &na)) {
+    GatherProblem ga = g, gb = g;
+    ga.dCf = gb.dCf = g.dC;
+    ga.dC = na; ga.n0 = 0;
+    gb.dC = g.dC - na; gb.n0 = na;
+    int n1 = 0, n2 = 0;
+    int rc = launch_gather(ga, x, w, y, nullptr, part, &n1, s);
+    if (rc != DP_OK) return rc;
+    rc = launch_gather(gb, x, w, y, nullptr, part, &n2, s);
+    if (rc != DP_OK) return rc;
+    if (nparts != nullptr) *nparts = n1;   // (== n2: fwd_split)
+    return DP_OK;
+  }
+  return launch_gather(g, x, w, y, nullptr, part, nparts, s, nullptr, nullptr, 1.f, 0, 1.f, nullptr, 0, fin);
 }
 
 bool tc_fwd_view_supported(const dp_conv_desc* d) { return tc_fwd_supported(d); }
@@ -1684,12 +1727,15 @@ int tc_describe_plan(const dp_conv_desc* d, int op, int has_stats, char* out, si
   TcPlan plan;
   if (!plan_gather(g, has_stats != 0, &plan, op == 1 && has_stats != 0)) return DP_ERR_UNSUPPORTED;
   const TcParams& p = plan.p;
+  int na = 0;   // forward: channels of the first of two launches when the output channels are split (0: one launch)
+  if (op == 0 && !fwd_split(g, has_stats != 0, &na)) na = 0;
   snprintf(out, n,
            "tile bw=%d bh=%d bt=%d MT=%d nloads=%d nsub=%d CB=%d ncblk=%d CBt=%d Ntile=%d n_ntiles=%d stages=%d lps=%d stage_bytes=%d "
-           "dual=%d acc_bufs=%d st_bufs=%d pub_sub=%d resident=%d reg_stats=%d mma_stats=%d drain_rs=%d tmem_cols=%d tiles=%d grid=%d smem=%zu",
+           "dual=%d acc_bufs=%d st_bufs=%d pub_sub=%d resident=%d reg_stats=%d mma_stats=%d drain_rs=%d tmem_cols=%d tiles=%d grid=%d smem=%zu "
+           "split=%d",
            p.bw, p.bh, p.bt, p.MT, p.nloads, p.nsub, p.CB, p.ncblk, p.CBt, p.Ntile, p.n_ntiles, p.num_stages, p.lps, p.stage_bytes,
            p.dual_mma, p.acc_bufs, p.st_bufs, p.pub_sub, p.w_resident, p.reg_stats, p.mma_stats, p.drain_rs, p.tmem_cols, p.num_tiles, plan.grid,
-           plan.smem);
+           plan.smem, na);
   return DP_OK;
 }
 
