@@ -511,6 +511,34 @@ def test_conv_tcgen05_plan_variants(opts):
             L.set_option(k, v)
 
 
+def test_conv_fwd_output_channel_split():
+    """Forward conv whose weights do not fit beside the pipeline (64 -> 144 channels, 9 taps): the output channels go in two
+    launches ([0, 80) and [80, 144)) with resident weights, into channel sub-ranges of the same destination and of the same
+    statistics partials.  dp_conv_describe_plan reports the split; output, padded channels and statistics over all 144
+    channels are checked against the fp64 convolution by the common checker (R2Plus1D.py:53, conv3/conv4 spatial convs)."""
+    import ctypes as C
+    lib = L.load()
+    default = L.get_option("tc_nsplit")
+    try:
+        for B, geom in ((8, GEOMS_BIG[3]), (16, GEOMS_BIG[5])):
+            Cc, K, k, s, p, T, H, W = geom
+            L.set_option("tc_nsplit", 2)      # 2: split whenever it makes the weights resident (1 also asks for >= 4 tiles per CTA)
+            o = [(n + 2 * p[i] - k[i]) // s[i] + 1 for i, n in enumerate((T, H, W))]
+            d = L.ConvDesc(B, T, H, W, Cc, Fn.ceil16(Cc), *o, K, Fn.ceil16(K), *k, *s, *p, L.DP_BF16)
+            buf = C.create_string_buffer(1024)
+            assert lib.dp_conv_describe_plan(C.byref(d), 0, 1, buf, 1024) == 0
+            assert " split=80" in buf.value.decode(), buf.value
+            n0 = lib.dp_launch_count()
+            res = _tc_check(geom, B=B, seed=11)
+            assert res["fwd"] < 2 ** -7 and res["sum"] < 1e-3 and res["sq"] < 1e-3, res
+            L.set_option("tc_nsplit", 0)
+            n1 = lib.dp_launch_count()
+            _tc_check(geom, B=B, seed=11)
+            assert (n1 - n0) - (lib.dp_launch_count() - n1) == 1, "the split forward is exactly one launch more"
+    finally:
+        L.set_option("tc_nsplit", default)
+
+
 def _fin_fwd(d, rows, gamma, beta, rm, rv, stats, ticket):
     return L.BnFin(kind=1, C=d.K, Cp=d.Kp, coef_zero=0, count=float(rows), gamma=gamma.data_ptr(), beta=beta.data_ptr(),
                    eps=1e-5, momentum=0.1, running_mean=rm.data_ptr(), running_var=rv.data_ptr(),
