@@ -86,6 +86,7 @@ struct TcParams {
   long long a_off_k[8];
   short dWk[8], dHk[8], dTk[8];
   int dbg_skip;  // development: 1 = no epilogue data movement / stores, 2 = no TMA loads, 4 = one MMA per load
+  int stats_keep;   // staged-tile statistics: per-thread sums live in registers across tiles (one N tile), combined once per CTA
   int pC, n_base;   // statistics partials: row pitch (channels of the full destination) and first channel of this launch
   int l2_hint;   // 1: activation boxes are loaded with an L2 evict-first policy (what the kernel WRITES outlives them in L2)
   long long a_off, a_sw, a_sh, a_st, a_sb;  // addend view: element offset / strides of (w,h,t,b) in the dst tensor
@@ -486,7 +487,12 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       lw[m] = em % p.bw; lh[m] = (em / p.bw) % p.bh; lt[m] = em / (p.bw * p.bh);
     }
     const uint32_t st_mask = (uint32_t)p.st_mask;
-    const bool legacy_stats = p.has_stats && !p.mma_stats && !STATS;
+    // (statistics outside the epilogue registers exist only in the generic-drain kernel: the planner gives them drain_rs == 0)
+    const bool legacy_stats = RS == 0 && p.has_stats && !p.mma_stats && !STATS;
+    const bool legacy_keep = legacy_stats && p.n_ntiles == 1 && p.stats_keep != 0;   // statistics of the staged tile kept in registers across tiles
+    float lsum[8], lsq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lsum[j] = 0.f; lsq[j] = 0.f; }
     const int st_bufs = p.st_bufs, bw_ = p.bw, bh_ = p.bh, bt_ = p.bt, dW_ = p.dW, dH_ = p.dH, dT_ = p.dT;
     int sbuf = 0;          // ring slot of the next sub-tile to stage
     uint32_t sub_idx = 0;  // sub-tiles staged so far
@@ -756,14 +762,19 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
       if (edbg) { const long long c2 = clock64(); w_c += c2 - c1; c1 = c2; }
       if (legacy_stats) {
-        // fallback (N tiles > 1): per-channel sum / sum of squares of the bf16 tile from the (unswizzled) staging tile
+        // tiles wider than the register / tensor-core statistics cover (N > 128, or several N tiles): per-channel sum / sum of
+        // squares of the bf16 tile from the (unswizzled) staging tile.  Thread (row group rg, 8-channel vector cv) keeps its
+        // sums in registers ACROSS tiles when every tile covers the same channels (one N tile): the row groups are combined
+        // once per CTA after the last tile instead of once per tile (scratch writes with 16-way bank conflicts, a second
+        // pass and two more barriers per tile: 4500 of the 7400 cycles a 64 -> 144 tile took, r2g_role_cycles.txt)
         const int row_bytes = p.st_rowbytes;
         const int ncv = p.Ntile >> 3;
         const int nrg = TC_EPI / ncv;
         const int cv = et % ncv, rg = et / ncv;
-        float sacc[8], qacc[8];
+        if (!legacy_keep) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { sacc[j] = 0.f; qacc[j] = 0.f; }
+          for (int j = 0; j < 8; ++j) { lsum[j] = 0.f; lsq[j] = 0.f; }
+        }
         if (rg < nrg) {
           for (int row = rg; row < 128; row += nrg) {
             const uint4 u = *reinterpret_cast<const uint4*>(staging + (size_t)row * row_bytes + cv * 16);
@@ -771,31 +782,33 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 fv = __bfloat1622float2(hh[j]);
-              sacc[2 * j] += fv.x; sacc[2 * j + 1] += fv.y;
-              qacc[2 * j] = fmaf(fv.x, fv.x, qacc[2 * j]); qacc[2 * j + 1] = fmaf(fv.y, fv.y, qacc[2 * j + 1]);
+              lsum[2 * j] += fv.x; lsum[2 * j + 1] += fv.y;
+              lsq[2 * j] = fmaf(fv.x, fv.x, lsq[2 * j]); lsq[2 * j + 1] = fmaf(fv.y, fv.y, lsq[2 * j + 1]);
             }
           }
         }
-        named_bar_sync(2, TC_EPI);                // previous tile's readers of scratch are done
-        if (rg < nrg) {
+        if (!legacy_keep) {
+          named_bar_sync(2, TC_EPI);                // previous tile's readers of scratch are done
+          if (rg < nrg) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            scratch[(rg * p.Ntile + cv * 8 + j) * 2 + 0] = sacc[j];
-            scratch[(rg * p.Ntile + cv * 8 + j) * 2 + 1] = qacc[j];
+            for (int j = 0; j < 8; ++j) {
+              scratch[(rg * p.Ntile + cv * 8 + j) * 2 + 0] = lsum[j];
+              scratch[(rg * p.Ntile + cv * 8 + j) * 2 + 1] = lsq[j];
+            }
           }
-        }
-        named_bar_sync(2, TC_EPI);
-        for (int c = et; c < p.Ntile; c += TC_EPI) {
-          float a0 = 0.f, b0 = 0.f;
-          for (int g = 0; g < nrg; ++g) {
-            a0 += scratch[(g * p.Ntile + c) * 2 + 0];
-            b0 += scratch[(g * p.Ntile + c) * 2 + 1];
+          named_bar_sync(2, TC_EPI);
+          for (int c = et; c < p.Ntile; c += TC_EPI) {
+            float a0 = 0.f, b0 = 0.f;
+            for (int g = 0; g < nrg; ++g) {
+              a0 += scratch[(g * p.Ntile + c) * 2 + 0];
+              b0 += scratch[(g * p.Ntile + c) * 2 + 1];
+            }
+            stats_sm[n_idx * p.Ntile + c] += a0;
+            stats_sm[p.dC + n_idx * p.Ntile + c] += b0;
           }
-          stats_sm[n_idx * p.Ntile + c] += a0;
-          stats_sm[p.dC + n_idx * p.Ntile + c] += b0;
         }
         // legacy statistics read the tile in place: the store warp releases the buffer (BAR_SFREE) only after ITS read,
-        // and the named barriers above order these readers before any thread can start the next drain into it
+        // and this barrier orders the readers before any thread can start the next drain into it
         named_bar_sync(2, TC_EPI);
       }
       if (edbg) { const long long c2 = clock64(); w_d += c2 - c1; c1 = c2; }
@@ -828,6 +841,28 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int g = 0; g < 4; ++g) { a0 += scratch[(g * p.Ntile + c) * 2 + 0]; b0 += scratch[(g * p.Ntile + c) * 2 + 1]; }
         prow[c] = a0;
         prow[p.pC + c] = b0;
+      }
+    }
+    if (legacy_keep) {   // combine the row groups once: scratch[rg][channel][2] -> stats_sm (zero so far)
+      const int ncv = p.Ntile >> 3;
+      const int nrg = TC_EPI / ncv;
+      const int cv = et % ncv, rg = et / ncv;
+      if (rg < nrg) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          scratch[(rg * p.Ntile + cv * 8 + j) * 2 + 0] = lsum[j];
+          scratch[(rg * p.Ntile + cv * 8 + j) * 2 + 1] = lsq[j];
+        }
+      }
+      named_bar_sync(2, TC_EPI);
+      for (int c = et; c < p.Ntile; c += TC_EPI) {
+        float a0 = 0.f, b0 = 0.f;
+        for (int g = 0; g < nrg; ++g) {
+          a0 += scratch[(g * p.Ntile + c) * 2 + 0];
+          b0 += scratch[(g * p.Ntile + c) * 2 + 1];
+        }
+        stats_sm[c] = a0;
+        stats_sm[p.dC + c] = b0;
       }
     }
     if (legacy_stats) {
@@ -901,7 +936,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64, g_opt_mt = 0, g_opt_classes = 1, g_opt_pub_sub_min = 64, g_opt_fine_n = 48, g_opt_l2hint = 0, g_opt_nsplit = 0;
+static int g_opt_halo = 1, g_opt_strided = 1, g_opt_max_stages = 8, g_opt_tc = 1, g_opt_mma_stats = 1, g_opt_resident = 1, g_opt_chunked = 1, g_opt_st_bufs = 2, g_opt_dbg_skip = 0, g_opt_lps_max = 16, g_opt_reg_stats = 1, g_opt_dual = 1, g_opt_tail = 1, g_opt_acc4 = 1, g_opt_bwd_stats_max = 64, g_opt_mt = 0, g_opt_classes = 1, g_opt_pub_sub_min = 64, g_opt_fine_n = 48, g_opt_l2hint = 0, g_opt_nsplit = 0, g_opt_stats_keep = 1;
 int tc_option(const char* name, int value, bool set) {
   int* slot = nullptr;
   if (!strcmp(name, "tc_halo")) slot = &g_opt_halo;
@@ -914,7 +949,8 @@ int tc_option(const char* name, int value, bool set) {
   else if (!strcmp(name, "tc_st_bufs")) slot = &g_opt_st_bufs;
   else if (!strcmp(name, "tc_dbg_skip")) slot = &g_opt_dbg_skip;
   else if (!strcmp(name, "tc_nsplit")) slot = &g_opt_nsplit;   // forward: output channels in two launches when that makes the weights resident
-  else if (!strcmp(name, "tc_l2hint")) slot = &g_opt_l2hint;   // evict-first loads of the activation operand
+  else if (!strcmp(name, "tc_l2hint")) slot = &g_opt_l2hint;
+  else if (!strcmp(name, "tc_stats_keep")) slot = &g_opt_stats_keep;   // evict-first loads of the activation operand
   else if (!strcmp(name, "tc_lps_max")) slot = &g_opt_lps_max;
   else if (!strcmp(name, "tc_reg_stats")) slot = &g_opt_reg_stats;
   else if (!strcmp(name, "tc_dual_mma")) slot = &g_opt_dual;
@@ -1366,6 +1402,7 @@ static int launch_gather(const GatherProblem& g, const void* src, const void* wg
              "tcgen05 conv: the fused BatchNorm epilogue excludes statistics");
   p.dbg_skip = g_opt_dbg_skip;
   p.l2_hint = g_opt_l2hint;
+  p.stats_keep = g_opt_stats_keep;
   const CUtensorMapSwizzle sw = p.CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                            : (p.CB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap tmA, tmB, tmD;

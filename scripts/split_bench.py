@@ -1,5 +1,7 @@
-"""Forward conv of the wide spatial layers at the bench batch: one launch (weights streamed per tile) against the
-output-channel split (two launches, resident weights) and against the two halves alone.  CUDA events, L2 flushed."""
+"""Forward conv (with BatchNorm statistics) of the wide spatial layers at the bench batch under the two values of one
+load-time option (OPT=tc_nsplit: one launch with weights streamed per tile against the output-channel split with
+resident weights; OPT=tc_stats_keep: staged-tile statistics combined per tile against once per CTA).  CUDA events, L2
+flushed between launches."""
 import os, sys, ctypes as C
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -24,8 +26,11 @@ def timeit(fn):
     return sorted(ts)[len(ts) // 2] * 1e3
 
 
+OPT = os.environ.get("OPT", "tc_nsplit")     # the option whose values 0 / 1 are compared
+
+
 def fwd_time(cin, cout, k, s, p, inp, nsplit):
-    L.set_option("tc_nsplit", nsplit)
+    L.set_option(OPT, nsplit)
     x = torch.randn(B, *inp, Fn.ceil16(cin), device=dev).bfloat16()
     gm = Fn.conv_geom(cin, cout, k, s, p, x)
     d = gm.desc
@@ -39,7 +44,7 @@ def fwd_time(cin, cout, k, s, p, inp, nsplit):
     lib.dp_conv_describe_plan(C.byref(d), 0, 1, buf, 1024)
     t = timeit(lambda: L.check(lib.dp_conv_fwd(C.byref(d), x.data_ptr(), wf.data_ptr(), y.data_ptr(), part.data_ptr(), C.byref(nparts), 0, st)))
     plan = buf.value.decode()
-    keys = ("MT=", "Ntile=", "resident=", "reg_stats=", "dual=", "stages=", "lps=", "split=")
+    keys = ("MT=", "Ntile=", "n_ntiles=", "resident=", "reg_stats=", "mma_stats=", "dual=", "stages=", "lps=", "split=")
     return t, " ".join(tok for tok in plan.split() if tok.startswith(keys))
 
 
@@ -52,5 +57,4 @@ for name, cin, cout, k, s, p, inp in (
         ("conv5 spatial 128->288", 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), (3, 8, 8))):
     for ns in (0, 1):
         t, plan = fwd_time(cin, cout, k, s, p, inp, ns)
-        print(f"{name:24s} tc_nsplit={ns}  {t:8.1f} us   {plan}", flush=True)
-L.set_option("tc_nsplit", 0)
+        print(f"{name:24s} {OPT}={ns}  {t:8.1f} us   {plan}", flush=True)
