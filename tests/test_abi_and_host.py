@@ -307,3 +307,40 @@ def test_plans_of_the_heavy_layers_keep_their_pipeline_shape():
         assert int(v["smem"]) <= 232448 and int(v["tmem_cols"]) <= 512 and v["grid"] == "148"
     # the structure behind dp_bn_fin: 4 int32, a double, 2 pointers, 2 floats, 10 pointers
     assert C.sizeof(L.BnFin) == 16 + 8 + 16 + 8 + 80
+
+
+def test_forward_channel_split_is_an_option_and_off_by_default():
+    """dp_conv_describe_plan (no device needed) reports the output-channel split of the forward conv: off by default
+    (measured neutral on the whole step); with `tc_nsplit` = 1 only the 64 -> 144 spatial convs whose
+    166 KB of weights do not fit beside the pipeline AND that have >= 4 tiles per CTA split (80 + 64 channels, both halves
+    resident on the same grid); layers with resident weights, or with several N tiles, never do."""
+    import ctypes as C
+    from dp_b200 import _lib as L
+    from dp_b200 import functional as Fn
+
+    lib = L.load()
+
+    def split_of(B, cin, cout, k, p, thw):
+        T, H, W = thw
+        o = [(n + 2 * p[i] - k[i]) + 1 for i, n in enumerate((T, H, W))]
+        d = L.ConvDesc(B, T, H, W, cin, Fn.ceil16(cin), *o, cout, Fn.ceil16(cout), *k, 1, 1, 1, *p, L.DP_BF16)
+        buf = C.create_string_buffer(1024)
+        assert lib.dp_conv_describe_plan(C.byref(d), 0, 1, buf, 1024) == 0, (cin, cout)
+        return int(dict(kv.split("=") for kv in buf.value.decode().split() if "=" in kv)["split"])
+
+    spatial, temporal = ((1, 3, 3), (0, 1, 1)), ((3, 1, 1), (1, 0, 0))
+    default = L.get_option("tc_nsplit")
+    try:
+        assert default == 0
+        assert split_of(64, 64, 144, *spatial, (11, 32, 32)) == 0
+        L.set_option("tc_nsplit", 1)
+        assert split_of(64, 64, 144, *spatial, (11, 32, 32)) == 80       # conv3 spatial: 5632 tiles
+        assert split_of(64, 64, 144, *spatial, (6, 16, 16)) == 80        # conv4 spatial: 768 tiles
+        assert split_of(2, 64, 144, *spatial, (11, 32, 32)) == 0         # 176 tiles: not worth a second launch
+        assert split_of(64, 32, 72, *spatial, (21, 64, 64)) == 0         # weights resident already
+        assert split_of(64, 144, 64, *temporal, (11, 32, 32)) == 0
+        assert split_of(64, 128, 288, *spatial, (3, 8, 8)) == 0          # two N tiles: not covered
+        L.set_option("tc_nsplit", 2)
+        assert split_of(2, 64, 144, *spatial, (11, 32, 32)) == 80        # 2: whenever the halves become resident (tests)
+    finally:
+        L.set_option("tc_nsplit", default)
