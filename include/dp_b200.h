@@ -106,8 +106,14 @@ unsigned long long dp_launch_count(void);
  * option "strict_tc" = 1 turns such a fallback into DP_ERR_UNSUPPORTED) */
 unsigned long long dp_simt_launch_count(void);
 unsigned long long dp_simt_fallback_count(void);
-/* tuning / debug switches: "tc_enable", "tc_halo", "tc_strided", "tc_max_stages", "tc_mma_stats", "tc_resident",
- * "wg_enable", "wg_halo", "wg_stack", "pdl" (programmatic dependent launch of the hot kernels) */
+/* tuning / debug switches (A/B measurements, tests; the defaults are the measured optimum): planner -- "tc_enable",
+ * "tc_halo", "tc_strided", "tc_classes", "tc_max_stages", "tc_lps_max", "tc_mt", "tc_dual_mma", "tc_fine_n", "tc_tail",
+ * "tc_acc4", "tc_st_bufs", "tc_pub_sub_min", "tc_resident", "tc_chunked", "tc_reg_stats", "tc_mma_stats",
+ * "tc_bwd_stats_max", "tc_stats_keep" (staged-tile statistics combined once per CTA, default 1), "tc_nsplit" (forward
+ * output channels in two launches with resident weights, default 0), "tc_l2hint" (evict-first activation loads,
+ * default 0), "wg_enable", "wg_halo", "wg_stack", "wg_items"; launch -- "pdl" / "pdl_small" (programmatic dependent
+ * launch of every kernel / of the small finalize and split-reduce kernels, default 0), "strict_tc"; BatchNorm passes --
+ * "bn_sweep" (traversal direction bits, default 0), "bn_cs" (streaming loads of dead operands, default 0) */
 int         dp_set_option(const char* name, int value);
 int         dp_get_option(const char* name);
 /* development / test aid: the tile, pipeline and statistics plan of the tcgen05 gather kernel for a forward (op 0) or
